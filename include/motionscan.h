@@ -1,0 +1,224 @@
+/*
+ * motionscan.h — C ABI of libmotionscan.so (B200 / sm_100a motion-scan hot path).
+ *
+ * Drop-in boundary for the motion-scan path of Motion-Estimated-Video-Trimmer.
+ * The reference exposes no FFI; the seam is cut where SURVEY.md §8(b) puts it.
+ * Citations are relative to the reference tree (/root/reference):
+ *
+ *   mscan_mv                <- AVMotionVector (FFmpeg libavutil/motion_vector.h), read at
+ *                              src/motion_scanner.cpp:224-226,243-256
+ *   mscan_params            <- cfg struct include/motion_trim/motion_scanner.hpp:86-93 filled at
+ *                              src/motion_scanner.cpp:184-196, + Config::max_gap_sec/padding_sec/
+ *                              min_savings_pct read at src/pipeline.cpp:333,337-338,358
+ *   mscan_segment           <- TimeSegment include/motion_trim/types.hpp:56-59
+ *   mscan_video_open        <- grid/margin derivation src/motion_scanner.cpp:189-199
+ *   mscan_submit            <- the per-frame call `check_frame(frame)` src/motion_scanner.cpp:376
+ *                              (decl include/motion_trim/motion_scanner.hpp:106), batched
+ *   mscan_collect           <- `if (has_motion) ts.push_back(pts)` src/motion_scanner.cpp:382-383
+ *   mscan_segments[_batch]  <- merge/segment/decision block src/pipeline.cpp:297-404
+ *                              (sort+unique :302-304, no-motion :308-319, builder :325-344,
+ *                              clamp+savings :349-356, decision :358-404)
+ *   mscan_scan_device / mscan_segments_device
+ *                           <- same two islands on caller-owned device memory (decode-free
+ *                              stream benchmark, BASELINE.json configs[4])
+ *
+ * Rules of the ABI: plain pointers and sizes, int status returns (0 = ok), no exceptions
+ * cross it, no CPU fallback exists behind it (a missing GPU is MSCAN_ERR_CUDA).
+ * Caller owns every host buffer; the library owns device memory, streams and pinned staging.
+ */
+#ifndef MOTIONSCAN_H
+#define MOTIONSCAN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCAN_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+enum {
+  MSCAN_OK = 0,
+  MSCAN_ERR_INVALID = 1,     /* bad argument / unknown video id / bad state       */
+  MSCAN_ERR_CUDA = 2,        /* CUDA runtime error or no usable device             */
+  MSCAN_ERR_NOMEM = 3,       /* host or device allocation failed                   */
+  MSCAN_ERR_CAPACITY = 4,    /* frame log / output buffer capacity exceeded        */
+  MSCAN_ERR_UNSUPPORTED = 5  /* geometry does not fit the kernel's shared memory   */
+};
+
+/* ---- decisions (src/pipeline.cpp:308-319,358-404) ---------------------- */
+enum {
+  MSCAN_NO_MOTION = 0, /* empty timestamp list: reference pushes no job, writes no file */
+  MSCAN_CUT = 1,       /* saved_pct >  MIN_SAVINGS_PCT: job carries the clamped segments */
+  MSCAN_FULL_COPY = 2  /* saved_pct <= MIN_SAVINGS_PCT: job carries [{0, duration}]      */
+};
+
+/* ---- record type: FFmpeg's native 40-byte AVMotionVector --------------- */
+typedef struct mscan_mv {
+  int32_t source;        /* @0  */
+  uint8_t w, h;          /* @4,@5 */
+  int16_t src_x, src_y;  /* @6,@8   read by the path */
+  int16_t dst_x, dst_y;  /* @10,@12 read by the path */
+  /* 2 bytes padding @14 */
+  uint64_t flags;        /* @16 */
+  int32_t motion_x;      /* @24 */
+  int32_t motion_y;      /* @28 */
+  uint16_t motion_scale; /* @32 */
+  /* 6 bytes padding → sizeof == 40 */
+} mscan_mv;
+
+/* ---- TimeSegment (include/motion_trim/types.hpp:56-59) ----------------- */
+typedef struct mscan_segment {
+  double start;
+  double end;
+} mscan_segment;
+
+/* ---- knobs (names = env vars of include/motion_trim/config.hpp:56-125) -- */
+typedef struct mscan_params {
+  double mv_threshold_sq;  /* MV_THRESHOLD_SQ  (code default 16.0)                     */
+  int32_t block_size;      /* BLOCK_SIZE       (16) — grid rounding only               */
+  int32_t block_shift;     /* BLOCK_SHIFT      (4)                                     */
+  int32_t vectors_needed;  /* VECTORS_NEEDED   (2) — wrapped to uint8 like config.hpp:75 */
+  int32_t clusters_needed; /* CLUSTERS_NEEDED  (2)                                     */
+  float vertical_mask;     /* VERTICAL_MASK    (0.05f), float32 like config.hpp:87     */
+  double max_gap_sec;      /* MAX_GAP_SEC      (5.0)                                   */
+  double padding_sec;      /* PADDING_SEC      (0.5)                                   */
+  double min_savings_pct;  /* MIN_SAVINGS_PCT  (5.0)                                   */
+} mscan_params;
+
+/* Per-video block-grid geometry (src/motion_scanner.cpp:189-196). */
+typedef struct mscan_geometry {
+  int32_t grid_w;          /* int16((width  + BLOCK_SIZE-1) >> BLOCK_SHIFT)            */
+  int32_t grid_h;          /* int16((height + BLOCK_SIZE-1) >> BLOCK_SHIFT)            */
+  int32_t vertical_margin; /* (int)(grid_h * VERTICAL_MASK), float32 multiply          */
+  int32_t reserved;
+} mscan_geometry;
+
+/* Result of the merge/segment/decision block for one video. */
+typedef struct mscan_video_result {
+  int32_t decision;         /* MSCAN_NO_MOTION / MSCAN_CUT / MSCAN_FULL_COPY           */
+  uint32_t n_motion_frames; /* timestamps after sort+unique (pipeline.cpp:302-304)      */
+  uint32_t n_segments;      /* motion segments built at pipeline.cpp:325-344            */
+  uint32_t reserved;
+  double out_dur;           /* Σ(end-start) after clamp, left-to-right (:350-354)       */
+  double time_removed;      /* duration - out_dur (:355)                                */
+  double saved_pct;         /* time_removed / duration * 100.0, or 0.0 (:356)           */
+} mscan_video_result;
+
+/* Per-context counters (bench.py reads these; times are CUDA-event milliseconds). */
+typedef struct mscan_stats {
+  uint64_t scan_launches;    /* K-A launches                                            */
+  uint64_t segment_launches; /* K-C launches                                            */
+  uint64_t aux_launches;     /* offset-scan / synth launches                            */
+  uint64_t frames_scanned;
+  uint64_t records_scanned;
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  double scan_ms;            /* Σ K-A durations, only while profiling is enabled         */
+  double segment_ms;         /* Σ K-C durations, only while profiling is enabled         */
+} mscan_stats;
+
+typedef struct mscan_ctx mscan_ctx;
+
+/* ---- library-level ----------------------------------------------------- */
+int mscan_abi_version(void);
+int mscan_device_count(int* n_out);            /* MSCAN_ERR_CUDA when no driver/GPU */
+const char* mscan_status_string(int status);
+
+/* config.hpp:56-125 code defaults */
+int mscan_params_default(mscan_params* p);
+/* defaults overridden by the reference's env vars; MSCAN_ERR_INVALID on unparsable values
+ * (the reference's std::stod/stoi would throw → terminate). */
+int mscan_params_from_env(mscan_params* p);
+/* motion_scanner.cpp:189-196 — pure host arithmetic, usable without a GPU */
+int mscan_geometry_from_dims(const mscan_params* p, int width, int height, mscan_geometry* g);
+
+/* ---- context (one per GPU; `submit` may be called from many threads) ---- */
+/* max_log_frames: capacity of the on-device frame log (0 → 16 Mi frames).
+ * slab_bytes: size of each of the 3 device record slabs + pinned staging (0 → 256 MiB). */
+int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uint64_t slab_bytes,
+                 mscan_ctx** ctx_out);
+int mscan_destroy(mscan_ctx* ctx);
+const char* mscan_last_error(mscan_ctx* ctx);
+int mscan_get_params(mscan_ctx* ctx, mscan_params* p_out);
+int mscan_sync(mscan_ctx* ctx);
+int mscan_get_stats(mscan_ctx* ctx, mscan_stats* s_out);
+int mscan_reset_stats(mscan_ctx* ctx);
+int mscan_set_profiling(mscan_ctx* ctx, int enabled); /* CUDA-event pairs around K-A / K-C */
+
+/* ---- host-fed path (pinned, double-buffered staging; memory_io.cpp role) */
+int mscan_video_open(mscan_ctx* ctx, uint32_t video_id, int width, int height);
+int mscan_video_open_geometry(mscan_ctx* ctx, uint32_t video_id, const mscan_geometry* g);
+/* Append n_frames frames of one video. recs holds the frames' records back to back in FFmpeg's
+ * native layout; rec_count[i] == 0 means "no MV side data" (motion_scanner.cpp:219-221).
+ * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / cudaHostRegister) it is DMA'd
+ * in place and must stay valid until mscan_flush/mscan_collect returns; pageable memory is
+ * copied into the library's pinned ring before the call returns. */
+int mscan_submit(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
+                 const uint32_t* rec_count, const mscan_mv* recs);
+int mscan_flush(mscan_ctx* ctx); /* launch whatever is staged; does not wait */
+/* Per-frame results in submission order. cap = capacity of flags/full_counts (either may be NULL). */
+int mscan_collect(mscan_ctx* ctx, uint32_t video_id, uint8_t* flags, uint32_t* full_counts,
+                  uint32_t cap, uint32_t* n_frames_out);
+/* Segments for the FFmpegJob of one video: on MSCAN_CUT the clamped motion segments, on
+ * MSCAN_FULL_COPY the single {0,duration}, on MSCAN_NO_MOTION none. MSCAN_ERR_CAPACITY if
+ * cap is too small (n_out still reports the needed count). */
+int mscan_segments(mscan_ctx* ctx, uint32_t video_id, double duration, mscan_segment* out,
+                   uint32_t cap, uint32_t* n_out, mscan_video_result* res_out);
+/* Same, but always the clamped motion segments of pipeline.cpp:325-354 whatever the decision. */
+int mscan_motion_segments(mscan_ctx* ctx, uint32_t video_id, double duration, mscan_segment* out,
+                          uint32_t cap, uint32_t* n_out, mscan_video_result* res_out);
+/* Many videos, one K-C launch. seg_off_out[n_videos+1] indexes out[]; job segments as above. */
+int mscan_segments_batch(mscan_ctx* ctx, uint32_t n_videos, const uint32_t* video_ids,
+                         const double* durations, mscan_segment* out, uint64_t cap,
+                         uint64_t* seg_off_out, mscan_video_result* res_out);
+int mscan_video_close(mscan_ctx* ctx, uint32_t video_id);
+
+/* pinned host memory for zero-copy submit */
+int mscan_host_alloc(mscan_ctx* ctx, size_t bytes, void** p_out);
+int mscan_host_free(mscan_ctx* ctx, void* p);
+
+/* ---- device-resident path (caller-owned device buffers) ---------------- */
+int mscan_dev_alloc(mscan_ctx* ctx, size_t bytes, void** d_out);
+int mscan_dev_free(mscan_ctx* ctx, void* d);
+int mscan_memcpy_h2d(mscan_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int mscan_memcpy_d2h(mscan_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* exclusive prefix sum: d_rec_off[0..n_frames] from d_rec_count[0..n_frames) */
+int mscan_offsets_from_counts(mscan_ctx* ctx, const uint32_t* d_rec_count, uint32_t n_frames,
+                              uint64_t* d_rec_off, void* stream);
+/* K-A on device memory. d_recs: 16-byte aligned; d_rec_off[n_frames+1] record indices into d_recs;
+ * d_frame_geom: per-frame index into geoms[] or NULL (all frames use geoms[0]).
+ * Asynchronous on `stream` (NULL → the context's scan stream). */
+int mscan_scan_device(mscan_ctx* ctx, const mscan_mv* d_recs, const uint64_t* d_rec_off,
+                      const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms,
+                      uint32_t n_frames, uint8_t* d_flags, uint32_t* d_full_counts, void* stream);
+/* K-C on device memory: video v owns frames [h_video_off[v], h_video_off[v+1]) of d_pts/d_flags.
+ * d_segments: capacity = h_video_off[n_videos] entries; video v's segments start at
+ * d_segments[h_video_off[v]]. d_results[n_videos]. Asynchronous on `stream`. */
+int mscan_segments_device(mscan_ctx* ctx, uint32_t n_videos, const uint64_t* h_video_off,
+                          const double* h_durations, const double* d_pts, const uint8_t* d_flags,
+                          mscan_segment* d_segments, mscan_video_result* d_results, void* stream);
+
+/* ---- measurement harness: deterministic synthetic MV streams ----------- */
+/* Spec and generator semantics: include/mvgen_core.h (same code on host and device). */
+struct mvgen_spec;
+/* presets for BASELINE.json configs[0..4] */
+int mscan_synth_preset(struct mvgen_spec* spec, int config, uint64_t seed);
+/* host generator (no GPU needed): counts, then records written at rec_off[] (record indices) */
+int mscan_synth_host_counts(const struct mvgen_spec* spec, uint64_t frame0, uint32_t n_frames,
+                            uint32_t* rec_count, int n_threads);
+int mscan_synth_host_fill(const struct mvgen_spec* spec, uint64_t frame0, uint32_t n_frames,
+                          const uint64_t* rec_off, mscan_mv* recs, double* pts, int n_threads);
+/* device generator, same bytes */
+int mscan_synth_counts(mscan_ctx* ctx, const struct mvgen_spec* spec, uint64_t frame0,
+                       uint32_t n_frames, uint32_t* d_rec_count, void* stream);
+int mscan_synth_fill(mscan_ctx* ctx, const struct mvgen_spec* spec, uint64_t frame0,
+                     uint32_t n_frames, const uint64_t* d_rec_off, mscan_mv* d_recs, double* d_pts,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOTIONSCAN_H */

@@ -1,0 +1,80 @@
+"""Builds libmotionscan.so (sm_100a) in-tree with nvcc. No torch extension machinery: the product is
+a plain C-ABI shared library (include/motionscan.h).
+
+    python motion-estimated-video-trimmer_b200/build.py [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+CSRC = HERE / "csrc"
+OUT = HERE / "libmotionscan.so"
+
+SOURCES = ["ka_scan.cu", "kc_segments.cu", "synth.cu", "synth_host.cu", "mscan_api.cu"]
+HEADERS = [CSRC / "common.cuh", CSRC / "kernels.cuh", ROOT / "include" / "motionscan.h", ROOT / "include" / "mvgen_core.h"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-fmad=false",                 # bit-exact f64 tail; the integer kernels have no float math
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-cudart", "static",           # self-contained: loads next to torch's own runtime
+    "--expt-relaxed-constexpr",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date() -> bool:
+    if not OUT.exists():
+        return False
+    t = OUT.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + HEADERS + [Path(__file__)]
+    return all(d.stat().st_mtime <= t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and up_to_date():
+        return OUT
+    objdir = HERE / "build"
+    objdir.mkdir(exist_ok=True)
+    objs = []
+    procs = []
+    for s in SOURCES:
+        o = objdir / (Path(s).stem + ".o")
+        cmd = [nvcc(), *NVCC_FLAGS, "-c", str(CSRC / s), "-o", str(o)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(o))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed on {s}\n{out}\n")
+        elif verbose or out.strip():
+            sys.stderr.write(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    cmd = [nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+           "-Xcompiler", "-fPIC", "-o", str(OUT), *objs, "-lpthread", "-ldl", "-lrt"]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(p)

@@ -1,0 +1,85 @@
+// kernels.cuh — host-callable launchers of the motion-scan kernels (internal to libmotionscan.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/motionscan.h"
+#include "../../include/mvgen_core.h"
+
+namespace mscan {
+
+constexpr int kRecBytes = 40;  // sizeof(AVMotionVector), src/motion_scanner.cpp:226
+
+// Geometry as the kernel consumes it: rows [y_min, y_max) are live (clamped to the grid).
+struct DevGeom {
+  int32_t gw, gh, y_min, y_max;
+};
+
+// ---- K-A: vote scatter + cluster count + activity flag (check_frame, motion_scanner.cpp:217-295)
+struct ScanArgs {
+  const uint8_t* recs;         // 16-byte aligned base of 40-byte records
+  const uint64_t* rec_off;     // [n_frames+1] record indices
+  const uint32_t* frame_geom;  // [n_frames] index into geoms, or nullptr → 0
+  const DevGeom* geoms;        // device table
+  uint8_t* flags;              // [n_frames]
+  uint32_t* counts;            // [n_frames] full cluster counts
+  uint32_t* work;              // work[0] = next frame, work[1] = finished CTAs (self-resetting)
+  uint32_t n_frames;
+  int32_t ithr;                // keep iff mag_sq >= ithr   (== !((double)mag_sq < T²))
+  int32_t keep_none;           // T² above INT32_MAX / +inf: nothing ever votes
+  int32_t shift;
+  uint32_t vec_need;           // uint8 VECTORS_NEEDED
+  uint32_t clust_need;         // max(1, CLUSTERS_NEEDED)
+  uint32_t stages;             // ring depth
+  uint32_t max_cells;          // counters in shared memory
+  uint32_t max_bit_words;      // words per bit-row buffer
+};
+
+struct ScanPlan {
+  uint32_t stages;
+  uint32_t smem_bytes;
+  uint32_t ctas_per_sm;
+};
+
+// Chooses ring depth / occupancy for the largest geometry; false if it cannot fit.
+bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan);
+cudaError_t scan_configure(uint32_t smem_optin);
+cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st);
+
+// ---- K-C: compaction + sort/unique + gap merge + savings + decision (pipeline.cpp:297-404)
+struct SegExtent {
+  uint64_t start;  // first frame index into pts/flags
+  uint64_t n;
+};
+struct SegJob {
+  uint32_t ext_begin, ext_end;  // extents of this video, in order
+  uint32_t reserved0, reserved1;
+  uint64_t ts_base;   // offset into ts scratch A/B (capacity = pow2 >= frames)
+  uint64_t ts_cap;    // power of two
+  uint64_t seg_base;  // offset into segment output
+  double duration;
+};
+struct SegArgs {
+  const SegJob* jobs;
+  const SegExtent* extents;
+  const double* pts;
+  const uint8_t* flags;
+  double* ts_a;
+  double* ts_b;
+  mscan_segment* segs;
+  mscan_video_result* results;
+  double max_gap, padding, min_savings_pct;
+};
+cudaError_t segments_launch(const SegArgs& a, uint32_t n_videos, cudaStream_t st);
+
+// ---- aux: exclusive scan of per-frame record counts, synthetic stream generation
+cudaError_t offsets_launch(const uint32_t* counts, uint32_t n, uint64_t* off, uint64_t* block_scratch,
+                           cudaStream_t st);
+uint32_t offsets_scratch_elems(uint32_t n);
+cudaError_t synth_counts_launch(const mvgen_spec& spec, uint64_t frame0, uint32_t n_frames, uint32_t* counts,
+                                cudaStream_t st);
+cudaError_t synth_fill_launch(const mvgen_spec& spec, uint64_t frame0, uint32_t n_frames, const uint64_t* rec_off,
+                              mscan_mv* recs, double* pts, cudaStream_t st);
+
+}  // namespace mscan

@@ -1,0 +1,1153 @@
+// mscan_api.cu — C ABI of libmotionscan.so (see include/motionscan.h for the reference citations).
+//
+// Host-side structure, per GPU context:
+//   * frame log   — device arrays pts/flags/counts indexed by "every frame ever submitted, in
+//                   order"; a video is a list of extents of the log (ResultCollector role,
+//                   reference src/task_queue.cpp:43-57);
+//   * slab ring   — 3 device record slabs, each with pinned host staging and its own stream:
+//                   while slab k is being DMA'd and scanned, submit() fills slab k+1
+//                   (memory_io.cpp role: the reference mmaps the file for FFmpeg; here the staged
+//                   thing is the decoder's MV side data on its way to HBM);
+//   * K-A per slab, K-C per segments call.
+// There is no CPU implementation of the path behind this ABI.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace mscan;
+
+namespace {
+
+constexpr int kSlabs = 3;
+constexpr int kWorkSlots = 16;
+constexpr uint32_t kMaxGeoms = 4096;
+
+struct Extent {
+  uint64_t start, n;
+};
+
+struct Video {
+  uint32_t geom = 0;
+  uint64_t n_frames = 0;
+  std::vector<Extent> extents;
+};
+
+struct Slab {
+  uint8_t* d_recs = nullptr;
+  uint8_t* h_recs = nullptr;  // pinned, allocated on first pageable submit
+  uint64_t* d_rec_off = nullptr;
+  uint64_t* h_rec_off = nullptr;
+  uint32_t* d_geom = nullptr;
+  uint32_t* h_geom = nullptr;
+  double* h_pts = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+  uint64_t bytes = 0;
+  uint64_t recs = 0;
+  uint32_t frames = 0;
+  uint64_t log_base = 0;
+};
+
+struct EvPair {
+  cudaEvent_t a, b;
+  int kind;  // 0 = K-A, 1 = K-C
+};
+
+}  // namespace
+
+struct mscan_ctx {
+  int device = 0;
+  int num_sms = 0;
+  uint32_t smem_optin = 0;
+  mscan_params params{};
+  std::mutex mu;
+  std::string err;
+
+  // kernel constants derived from params
+  int32_t ithr = 0;
+  int32_t keep_none = 0;
+  uint32_t vec_need = 0;
+  uint32_t clust_need = 1;
+
+  // geometry table
+  std::vector<DevGeom> geoms;
+  DevGeom* d_geoms = nullptr;
+  uint32_t max_cells = 0, max_bit_words = 0;
+  ScanPlan plan{};
+
+  // frame log
+  uint64_t log_cap = 0, log_head = 0;
+  double* d_pts = nullptr;
+  uint8_t* d_flags = nullptr;
+  uint32_t* d_counts = nullptr;
+
+  // slabs
+  uint64_t slab_bytes = 0;
+  uint32_t slab_frames = 0;
+  Slab slabs[kSlabs];
+  int cur = 0;
+
+  uint32_t* d_work = nullptr;  // kWorkSlots × {next, done}
+  uint32_t work_rr = 0;
+
+  cudaStream_t main_stream = nullptr;
+  std::map<uint32_t, Video> videos;
+
+  // K-C scratch (grown on demand)
+  uint64_t ts_cap = 0;
+  double *d_ts_a = nullptr, *d_ts_b = nullptr;
+  uint64_t seg_cap = 0;
+  mscan_segment* d_segs = nullptr;
+  uint32_t job_cap = 0, ext_cap = 0;
+  SegJob *d_jobs = nullptr, *h_jobs = nullptr;
+  SegExtent *d_exts = nullptr, *h_exts = nullptr;
+  mscan_video_result *d_res = nullptr, *h_res = nullptr;
+  // geometry staging for the device API
+  DevGeom* d_user_geoms = nullptr;
+  uint32_t user_geoms_cap = 0;
+
+  mscan_stats stats{};
+  bool profiling = false;
+  std::vector<EvPair> ev_pending;
+  std::vector<EvPair> ev_free;
+};
+
+namespace {
+
+int fail(mscan_ctx* c, int code, const char* fmt, ...) {
+  if (c) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    c->err = buf;
+  }
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, MSCAN_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// keep iff !((double)mag_sq < T²)  (motion_scanner.cpp:251)  ⇔  mag_sq >= ceil(T²) for finite T²
+void threshold_to_int(double t2, int32_t* ithr, int32_t* keep_none) {
+  *keep_none = 0;
+  if (std::isnan(t2)) {  // every `<` against NaN is false → everything is kept
+    *ithr = std::numeric_limits<int32_t>::min();
+    return;
+  }
+  const double c = std::ceil(t2);
+  if (c > 2147483647.0) {  // also +inf: no int32 magnitude reaches it
+    *ithr = std::numeric_limits<int32_t>::max();
+    *keep_none = 1;
+  } else if (c <= -2147483648.0) {
+    *ithr = std::numeric_limits<int32_t>::min();
+  } else {
+    *ithr = (int32_t)c;
+  }
+}
+
+DevGeom to_dev_geom(const mscan_geometry& g) {
+  DevGeom d;
+  d.gw = g.grid_w;
+  d.gh = g.grid_h;
+  // rows [margin, gh-margin) are live (:237-238); clamp to the grid (margin < 0 or 2*margin > gh is
+  // out-of-bounds behaviour in the reference, outside the parity domain)
+  int y0 = g.vertical_margin, y1 = g.grid_h - g.vertical_margin;
+  y0 = std::max(0, std::min(y0, g.grid_h));
+  y1 = std::max(y0, std::min(y1, g.grid_h));
+  d.y_min = y0;
+  d.y_max = y1;
+  return d;
+}
+
+bool geom_ok(const mscan_geometry& g) { return g.grid_w >= 0 && g.grid_h >= 0 && g.grid_w <= 32767 && g.grid_h <= 32767; }
+
+void geom_need(const DevGeom& g, uint32_t* cells, uint32_t* bit_words) {
+  *cells = (uint32_t)g.gw * (uint32_t)g.gh;
+  *bit_words = (uint32_t)g.gh * (((uint32_t)g.gw + 31u) >> 5);
+}
+
+EvPair get_events(mscan_ctx* c, int kind) {
+  EvPair p{};
+  if (!c->ev_free.empty()) {
+    p = c->ev_free.back();
+    c->ev_free.pop_back();
+  } else {
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+  }
+  p.kind = kind;
+  return p;
+}
+
+void drain_events(mscan_ctx* c) {
+  for (auto& p : c->ev_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      if (p.kind == 0) c->stats.scan_ms += ms;
+      else c->stats.segment_ms += ms;
+    }
+    c->ev_free.push_back(p);
+  }
+  c->ev_pending.clear();
+}
+
+int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaStream_t st, uint64_t n_recs) {
+  ScanArgs a = args_in;
+  a.work = c->d_work + 2 * (c->work_rr++ % kWorkSlots);
+  EvPair ev{};
+  if (c->profiling) {
+    ev = get_events(c, 0);
+    cudaEventRecord(ev.a, st);
+  }
+  CU(scan_launch(a, plan, c->num_sms, st));
+  if (c->profiling) {
+    cudaEventRecord(ev.b, st);
+    c->ev_pending.push_back(ev);
+  }
+  c->stats.scan_launches += 1;
+  c->stats.frames_scanned += a.n_frames;
+  c->stats.records_scanned += n_recs;
+  return MSCAN_OK;
+}
+
+ScanArgs base_args(mscan_ctx* c) {
+  ScanArgs a{};
+  a.ithr = c->ithr;
+  a.keep_none = c->keep_none;
+  a.shift = c->params.block_shift;
+  a.vec_need = c->vec_need;
+  a.clust_need = c->clust_need;
+  return a;
+}
+
+// launch K-A on whatever the current slab holds
+int launch_slab(mscan_ctx* c, Slab& s) {
+  if (s.frames == 0) return MSCAN_OK;
+  s.h_rec_off[s.frames] = s.recs;
+  CU(cudaMemcpyAsync(s.d_rec_off, s.h_rec_off, sizeof(uint64_t) * (s.frames + 1), cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(s.d_geom, s.h_geom, sizeof(uint32_t) * s.frames, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(c->d_pts + s.log_base, s.h_pts, sizeof(double) * s.frames, cudaMemcpyHostToDevice, s.stream));
+  c->stats.h2d_bytes += sizeof(uint64_t) * (s.frames + 1) + 12ull * s.frames;
+  ScanArgs a = base_args(c);
+  a.recs = s.d_recs;
+  a.rec_off = s.d_rec_off;
+  a.frame_geom = s.d_geom;
+  a.geoms = c->d_geoms;
+  a.flags = c->d_flags + s.log_base;
+  a.counts = c->d_counts + s.log_base;
+  a.n_frames = s.frames;
+  a.stages = c->plan.stages;
+  a.max_cells = c->max_cells;
+  a.max_bit_words = c->max_bit_words;
+  int rc = run_scan(c, a, c->plan, s.stream, s.recs);
+  if (rc) return rc;
+  CU(cudaEventRecord(s.done, s.stream));
+  s.in_flight = true;
+  return MSCAN_OK;
+}
+
+int wait_slab(mscan_ctx* c, Slab& s) {
+  if (s.in_flight) {
+    CU(cudaEventSynchronize(s.done));
+    s.in_flight = false;
+  }
+  s.bytes = 0;
+  s.recs = 0;
+  s.frames = 0;
+  return MSCAN_OK;
+}
+
+int flush_locked(mscan_ctx* c) {
+  Slab& s = c->slabs[c->cur];
+  if (s.frames == 0 || s.in_flight) return MSCAN_OK;
+  int rc = launch_slab(c, s);
+  if (rc) return rc;
+  c->cur = (c->cur + 1) % kSlabs;
+  return wait_slab(c, c->slabs[c->cur]);
+}
+
+int sync_scans_locked(mscan_ctx* c) {
+  int rc = flush_locked(c);
+  if (rc) return rc;
+  for (auto& s : c->slabs)
+    if (s.in_flight) {
+      CU(cudaEventSynchronize(s.done));
+      s.in_flight = false;
+      if (&s != &c->slabs[c->cur]) {
+        s.bytes = 0;
+        s.recs = 0;
+        s.frames = 0;
+      }
+    }
+  return MSCAN_OK;
+}
+
+int replan(mscan_ctx* c) {
+  ScanPlan p;
+  if (!scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, &p))
+    return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells does not fit shared memory", c->max_cells);
+  c->plan = p;
+  return MSCAN_OK;
+}
+
+int add_geometry(mscan_ctx* c, const mscan_geometry& g, uint32_t* idx) {
+  if (!geom_ok(g)) return fail(c, MSCAN_ERR_INVALID, "bad geometry %dx%d", g.grid_w, g.grid_h);
+  const DevGeom d = to_dev_geom(g);
+  for (uint32_t i = 0; i < c->geoms.size(); ++i) {
+    const DevGeom& e = c->geoms[i];
+    if (e.gw == d.gw && e.gh == d.gh && e.y_min == d.y_min && e.y_max == d.y_max) {
+      *idx = i;
+      return MSCAN_OK;
+    }
+  }
+  if (c->geoms.size() >= kMaxGeoms) return fail(c, MSCAN_ERR_CAPACITY, "too many distinct geometries");
+  uint32_t cells, words;
+  geom_need(d, &cells, &words);
+  const uint32_t old_cells = c->max_cells, old_words = c->max_bit_words;
+  c->max_cells = std::max(c->max_cells, cells);
+  c->max_bit_words = std::max(c->max_bit_words, words);
+  if (c->max_cells != old_cells || c->max_bit_words != old_words) {
+    int rc = replan(c);
+    if (rc) {
+      c->max_cells = old_cells;
+      c->max_bit_words = old_words;
+      return rc;
+    }
+  }
+  *idx = (uint32_t)c->geoms.size();
+  c->geoms.push_back(d);
+  // the table is only appended to; in-flight kernels never read the new slot
+  CU(cudaMemcpyAsync(c->d_geoms + *idx, &c->geoms[*idx], sizeof(DevGeom), cudaMemcpyHostToDevice, c->main_stream));
+  CU(cudaStreamSynchronize(c->main_stream));
+  return MSCAN_OK;
+}
+
+template <typename T>
+int grow(mscan_ctx* c, T** d, uint64_t* cap, uint64_t need) {
+  if (need <= *cap) return MSCAN_OK;
+  uint64_t n = std::max<uint64_t>(need, *cap * 2);
+  if (*d) cudaFree(*d);
+  *d = nullptr;
+  *cap = 0;
+  if (cudaMalloc((void**)d, n * sizeof(T)) != cudaSuccess) return fail(c, MSCAN_ERR_NOMEM, "cudaMalloc of %llu bytes failed", (unsigned long long)(n * sizeof(T)));
+  *cap = n;
+  return MSCAN_OK;
+}
+
+uint64_t pow2_ge(uint64_t n) {
+  uint64_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mscan_abi_version(void) { return MSCAN_ABI_VERSION; }
+
+const char* mscan_status_string(int s) {
+  switch (s) {
+    case MSCAN_OK: return "ok";
+    case MSCAN_ERR_INVALID: return "invalid argument or state";
+    case MSCAN_ERR_CUDA: return "CUDA error / no usable GPU";
+    case MSCAN_ERR_NOMEM: return "out of memory";
+    case MSCAN_ERR_CAPACITY: return "capacity exceeded";
+    case MSCAN_ERR_UNSUPPORTED: return "unsupported geometry";
+    default: return "unknown status";
+  }
+}
+
+int mscan_device_count(int* n_out) {
+  if (!n_out) return MSCAN_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    *n_out = 0;
+    return MSCAN_ERR_CUDA;
+  }
+  *n_out = n;
+  return n > 0 ? MSCAN_OK : MSCAN_ERR_CUDA;
+}
+
+int mscan_params_default(mscan_params* p) {
+  if (!p) return MSCAN_ERR_INVALID;
+  p->mv_threshold_sq = 16.0;  // config.hpp:57
+  p->block_size = 16;         // :63
+  p->block_shift = 4;         // :69
+  p->vectors_needed = 2;      // :75
+  p->clusters_needed = 2;     // :81
+  p->vertical_mask = 0.05f;   // :87
+  p->max_gap_sec = 5.0;       // :93
+  p->padding_sec = 0.5;       // :99
+  p->min_savings_pct = 5.0;   // :123
+  return MSCAN_OK;
+}
+
+static bool env_double(const char* name, double* v) {
+  const char* s = std::getenv(name);
+  if (!s) return true;
+  char* end = nullptr;
+  const double x = std::strtod(s, &end);  // std::stod: leading whitespace ok, trailing junk ignored
+  if (end == s) return false;
+  *v = x;
+  return true;
+}
+static bool env_int(const char* name, int32_t* v) {
+  const char* s = std::getenv(name);
+  if (!s) return true;
+  char* end = nullptr;
+  const long x = std::strtol(s, &end, 10);
+  if (end == s) return false;
+  *v = (int32_t)x;
+  return true;
+}
+static bool env_float(const char* name, float* v) {
+  const char* s = std::getenv(name);
+  if (!s) return true;
+  char* end = nullptr;
+  const float x = std::strtof(s, &end);
+  if (end == s) return false;
+  *v = x;
+  return true;
+}
+
+int mscan_params_from_env(mscan_params* p) {
+  int rc = mscan_params_default(p);
+  if (rc) return rc;
+  bool ok = true;
+  ok &= env_double("MV_THRESHOLD_SQ", &p->mv_threshold_sq);
+  ok &= env_int("BLOCK_SIZE", &p->block_size);
+  ok &= env_int("BLOCK_SHIFT", &p->block_shift);
+  ok &= env_int("VECTORS_NEEDED", &p->vectors_needed);
+  ok &= env_int("CLUSTERS_NEEDED", &p->clusters_needed);
+  ok &= env_float("VERTICAL_MASK", &p->vertical_mask);
+  ok &= env_double("MAX_GAP_SEC", &p->max_gap_sec);
+  ok &= env_double("PADDING_SEC", &p->padding_sec);
+  ok &= env_double("MIN_SAVINGS_PCT", &p->min_savings_pct);
+  return ok ? MSCAN_OK : MSCAN_ERR_INVALID;
+}
+
+int mscan_geometry_from_dims(const mscan_params* p, int width, int height, mscan_geometry* g) {
+  if (!p || !g) return MSCAN_ERR_INVALID;
+  if (p->block_shift < 0 || p->block_shift > 30) return MSCAN_ERR_INVALID;
+  // motion_scanner.cpp:189-192: int arithmetic narrowed to int16_t
+  const int16_t gw = (int16_t)((width + p->block_size - 1) >> p->block_shift);
+  const int16_t gh = (int16_t)((height + p->block_size - 1) >> p->block_shift);
+  g->grid_w = gw;
+  g->grid_h = gh;
+  // :196 — int16 → float, float32 multiply, truncate toward zero
+  volatile float prod = (float)gh * p->vertical_mask;
+  g->vertical_margin = (int)prod;
+  g->reserved = 0;
+  return MSCAN_OK;
+}
+
+int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uint64_t slab_bytes, mscan_ctx** out) {
+  if (!p || !out) return MSCAN_ERR_INVALID;
+  *out = nullptr;
+  if (p->block_shift < 0 || p->block_shift > 30) return MSCAN_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return MSCAN_ERR_CUDA;  // no CPU fallback
+  }
+  mscan_ctx* c = new (std::nothrow) mscan_ctx();
+  if (!c) return MSCAN_ERR_NOMEM;
+  c->device = device;
+  c->params = *p;
+  threshold_to_int(p->mv_threshold_sq, &c->ithr, &c->keep_none);
+  c->vec_need = (uint32_t)(uint8_t)p->vectors_needed;  // config.hpp:75 static_cast<uint8_t>
+  c->clust_need = p->clusters_needed < 1 ? 1u : (uint32_t)p->clusters_needed;
+  c->log_cap = max_log_frames ? max_log_frames : (16ull << 20);
+  c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (256ull << 20);
+  c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
+
+  auto bail = [&](int code) {
+    mscan_destroy(c);
+    return code;
+  };
+#define CUB_(call)                                         \
+  do {                                                     \
+    if ((call) != cudaSuccess) {                           \
+      cudaGetLastError();                                  \
+      return bail(MSCAN_ERR_CUDA);                         \
+    }                                                      \
+  } while (0)
+  CUB_(cudaSetDevice(device));
+  int v = 0;
+  CUB_(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  c->num_sms = v;
+  CUB_(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  c->smem_optin = (uint32_t)v;
+  CUB_(scan_configure(c->smem_optin));
+  CUB_(cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
+  CUB_(cudaMalloc((void**)&c->d_geoms, sizeof(DevGeom) * kMaxGeoms));
+  CUB_(cudaMalloc((void**)&c->d_work, sizeof(uint32_t) * 2 * kWorkSlots));
+  CUB_(cudaMemset(c->d_work, 0, sizeof(uint32_t) * 2 * kWorkSlots));
+  CUB_(cudaMalloc((void**)&c->d_pts, sizeof(double) * c->log_cap));
+  CUB_(cudaMalloc((void**)&c->d_flags, c->log_cap));
+  CUB_(cudaMalloc((void**)&c->d_counts, sizeof(uint32_t) * c->log_cap));
+  for (auto& s : c->slabs) {
+    CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CUB_(cudaMalloc((void**)&s.d_recs, c->slab_bytes + 256));
+    CUB_(cudaMalloc((void**)&s.d_rec_off, sizeof(uint64_t) * (c->slab_frames + 1)));
+    CUB_(cudaMalloc((void**)&s.d_geom, sizeof(uint32_t) * c->slab_frames));
+    CUB_(cudaHostAlloc((void**)&s.h_rec_off, sizeof(uint64_t) * (c->slab_frames + 1), cudaHostAllocDefault));
+    CUB_(cudaHostAlloc((void**)&s.h_geom, sizeof(uint32_t) * c->slab_frames, cudaHostAllocDefault));
+    CUB_(cudaHostAlloc((void**)&s.h_pts, sizeof(double) * c->slab_frames, cudaHostAllocDefault));
+  }
+#undef CUB_
+  *out = c;
+  return MSCAN_OK;
+}
+
+int mscan_destroy(mscan_ctx* c) {
+  if (!c) return MSCAN_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& p : c->ev_pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto& p : c->ev_free) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  for (auto& s : c->slabs) {
+    if (s.d_recs) cudaFree(s.d_recs);
+    if (s.h_recs) cudaFreeHost(s.h_recs);
+    if (s.d_rec_off) cudaFree(s.d_rec_off);
+    if (s.h_rec_off) cudaFreeHost(s.h_rec_off);
+    if (s.d_geom) cudaFree(s.d_geom);
+    if (s.h_geom) cudaFreeHost(s.h_geom);
+    if (s.h_pts) cudaFreeHost(s.h_pts);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaFree(c->d_geoms);
+  cudaFree(c->d_work);
+  cudaFree(c->d_pts);
+  cudaFree(c->d_flags);
+  cudaFree(c->d_counts);
+  cudaFree(c->d_ts_a);
+  cudaFree(c->d_ts_b);
+  cudaFree(c->d_segs);
+  cudaFree(c->d_jobs);
+  cudaFree(c->d_exts);
+  cudaFree(c->d_res);
+  cudaFree(c->d_user_geoms);
+  if (c->h_jobs) cudaFreeHost(c->h_jobs);
+  if (c->h_exts) cudaFreeHost(c->h_exts);
+  if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->main_stream) cudaStreamDestroy(c->main_stream);
+  cudaGetLastError();
+  delete c;
+  return MSCAN_OK;
+}
+
+const char* mscan_last_error(mscan_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int mscan_get_params(mscan_ctx* c, mscan_params* p) {
+  if (!c || !p) return MSCAN_ERR_INVALID;
+  *p = c->params;
+  return MSCAN_OK;
+}
+
+int mscan_sync(mscan_ctx* c) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  int rc = sync_scans_locked(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->main_stream));
+  return MSCAN_OK;
+}
+
+int mscan_get_stats(mscan_ctx* c, mscan_stats* s) {
+  if (!c || !s) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  drain_events(c);
+  *s = c->stats;
+  return MSCAN_OK;
+}
+
+int mscan_reset_stats(mscan_ctx* c) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  cudaSetDevice(c->device);
+  drain_events(c);
+  c->stats = mscan_stats{};
+  return MSCAN_OK;
+}
+
+int mscan_set_profiling(mscan_ctx* c, int enabled) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->profiling = enabled != 0;
+  return MSCAN_OK;
+}
+
+// ---- host-fed path ------------------------------------------------------------------------------
+int mscan_video_open_geometry(mscan_ctx* c, uint32_t video_id, const mscan_geometry* g) {
+  if (!c || !g) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  if (c->videos.count(video_id)) return fail(c, MSCAN_ERR_INVALID, "video %u already open", video_id);
+  // a larger grid changes the kernel's shared-memory plan: finish what is staged under the old one
+  uint32_t idx = 0;
+  const uint32_t old_cells = c->max_cells;
+  {
+    uint32_t cells, words;
+    if (!geom_ok(*g)) return fail(c, MSCAN_ERR_INVALID, "bad geometry %dx%d", g->grid_w, g->grid_h);
+    geom_need(to_dev_geom(*g), &cells, &words);
+    if (cells > old_cells) {
+      int rc = flush_locked(c);
+      if (rc) return rc;
+    }
+  }
+  int rc = add_geometry(c, *g, &idx);
+  if (rc) return rc;
+  Video v;
+  v.geom = idx;
+  c->videos.emplace(video_id, std::move(v));
+  return MSCAN_OK;
+}
+
+int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
+  if (!c) return MSCAN_ERR_INVALID;
+  mscan_geometry g;
+  int rc = mscan_geometry_from_dims(&c->params, width, height, &g);
+  if (rc) return fail(c, rc, "bad dimensions %dx%d", width, height);
+  return mscan_video_open_geometry(c, video_id, &g);
+}
+
+int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                 const mscan_mv* recs) {
+  if (!c) return MSCAN_ERR_INVALID;
+  if (n_frames == 0) return MSCAN_OK;
+  if (!pts || !rec_count) return fail(c, MSCAN_ERR_INVALID, "null pts/rec_count");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  Video& v = it->second;
+  if (c->log_head + n_frames > c->log_cap) {
+    if (c->videos.size() == 1 && v.n_frames == 0 && n_frames <= c->log_cap) {
+      int rc = sync_scans_locked(c);
+      if (rc) return rc;
+      c->log_head = 0;  // nothing else lives in the log
+    } else {
+      return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames); close videos or create a larger context",
+                  (unsigned long long)c->log_cap);
+    }
+  }
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(recs);
+  const bool pinned = recs && is_pinned(recs);
+  uint32_t f = 0;
+  uint64_t src_rec = 0;
+  while (f < n_frames) {
+    Slab* s = &c->slabs[c->cur];
+    // how many whole frames fit into the current slab
+    uint32_t take = 0;
+    uint64_t take_recs = 0;
+    while (f + take < n_frames && s->frames + take < c->slab_frames) {
+      const uint64_t nb = (take_recs + rec_count[f + take]) * (uint64_t)kRecBytes;
+      if (s->bytes + nb > c->slab_bytes) break;
+      take_recs += rec_count[f + take];
+      ++take;
+    }
+    if (take == 0) {
+      if (s->frames == 0) {
+        return fail(c, MSCAN_ERR_CAPACITY, "frame with %u records exceeds the slab size (%llu bytes)", rec_count[f],
+                    (unsigned long long)c->slab_bytes);
+      }
+      int rc = flush_locked(c);
+      if (rc) return rc;
+      continue;
+    }
+    if (s->frames == 0) s->log_base = c->log_head;
+    const uint64_t nbytes = take_recs * (uint64_t)kRecBytes;
+    if (nbytes) {
+      if (!recs) return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
+      const uint8_t* from = src + src_rec * (uint64_t)kRecBytes;
+      if (pinned) {
+        CU(cudaMemcpyAsync(s->d_recs + s->bytes, from, nbytes, cudaMemcpyHostToDevice, s->stream));
+      } else {
+        if (!s->h_recs) CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
+        std::memcpy(s->h_recs + s->bytes, from, nbytes);
+        CU(cudaMemcpyAsync(s->d_recs + s->bytes, s->h_recs + s->bytes, nbytes, cudaMemcpyHostToDevice, s->stream));
+      }
+      c->stats.h2d_bytes += nbytes;
+    }
+    uint64_t r = s->recs;
+    for (uint32_t i = 0; i < take; ++i) {
+      s->h_rec_off[s->frames + i] = r;
+      r += rec_count[f + i];
+      s->h_geom[s->frames + i] = v.geom;
+      s->h_pts[s->frames + i] = pts[f + i];
+    }
+    // extend the video's last extent when contiguous in the log
+    const uint64_t at = c->log_head;
+    if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == at) v.extents.back().n += take;
+    else v.extents.push_back(Extent{at, take});
+    v.n_frames += take;
+    c->log_head += take;
+    s->frames += take;
+    s->recs += take_recs;
+    s->bytes += nbytes;
+    src_rec += take_recs;
+    f += take;
+    if (s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes) {
+      int rc = flush_locked(c);
+      if (rc) return rc;
+    }
+  }
+  return MSCAN_OK;
+}
+
+int mscan_flush(mscan_ctx* c) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  return flush_locked(c);
+}
+
+int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  const Video& v = it->second;
+  if (n_out) *n_out = (uint32_t)v.n_frames;
+  if (v.n_frames > cap && (flags || counts)) return fail(c, MSCAN_ERR_CAPACITY, "need room for %llu frames", (unsigned long long)v.n_frames);
+  int rc = sync_scans_locked(c);
+  if (rc) return rc;
+  uint64_t at = 0;
+  for (const Extent& e : v.extents) {
+    if (flags) CU(cudaMemcpyAsync(flags + at, c->d_flags + e.start, e.n, cudaMemcpyDeviceToHost, c->main_stream));
+    if (counts) CU(cudaMemcpyAsync(counts + at, c->d_counts + e.start, e.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
+    c->stats.d2h_bytes += (flags ? e.n : 0) + (counts ? 4 * e.n : 0);
+    at += e.n;
+  }
+  CU(cudaStreamSynchronize(c->main_stream));
+  return MSCAN_OK;
+}
+
+// Runs K-C for a list of open videos; leaves results in c->h_res and segments on the device.
+static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
+                               std::vector<uint64_t>* seg_base_out) {
+  int rc = sync_scans_locked(c);
+  if (rc) return rc;
+  uint64_t n_ext = 0, ts_total = 0, seg_total = 0;
+  for (uint32_t i = 0; i < n_videos; ++i) {
+    auto it = c->videos.find(ids[i]);
+    if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", ids[i]);
+    n_ext += it->second.extents.size();
+    ts_total += pow2_ge(std::max<uint64_t>(it->second.n_frames, 1));
+    seg_total += std::max<uint64_t>(it->second.n_frames, 1);
+  }
+  if (n_videos > c->job_cap) {
+    if (c->h_jobs) cudaFreeHost(c->h_jobs);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    cudaFree(c->d_jobs);
+    cudaFree(c->d_res);
+    c->job_cap = 0;
+    const uint32_t n = std::max(n_videos, 64u);
+    CU(cudaHostAlloc((void**)&c->h_jobs, sizeof(SegJob) * n, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&c->h_res, sizeof(mscan_video_result) * n, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&c->d_jobs, sizeof(SegJob) * n));
+    CU(cudaMalloc((void**)&c->d_res, sizeof(mscan_video_result) * n));
+    c->job_cap = n;
+  }
+  if (n_ext > c->ext_cap) {
+    if (c->h_exts) cudaFreeHost(c->h_exts);
+    cudaFree(c->d_exts);
+    c->ext_cap = 0;
+    const uint32_t n = (uint32_t)std::max<uint64_t>(n_ext, 256);
+    CU(cudaHostAlloc((void**)&c->h_exts, sizeof(SegExtent) * n, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&c->d_exts, sizeof(SegExtent) * n));
+    c->ext_cap = n;
+  }
+  {
+    uint64_t cap = c->ts_cap;
+    rc = grow(c, &c->d_ts_a, &cap, ts_total);
+    if (rc) return rc;
+    uint64_t cap_b = c->ts_cap;
+    rc = grow(c, &c->d_ts_b, &cap_b, ts_total);
+    if (rc) return rc;
+    c->ts_cap = std::min(cap, cap_b);
+    rc = grow(c, &c->d_segs, &c->seg_cap, seg_total);
+    if (rc) return rc;
+  }
+  seg_base_out->resize(n_videos);
+  uint64_t e = 0, ts_at = 0, seg_at = 0;
+  for (uint32_t i = 0; i < n_videos; ++i) {
+    const Video& v = c->videos.find(ids[i])->second;
+    SegJob j{};
+    j.ext_begin = (uint32_t)e;
+    for (const Extent& x : v.extents) c->h_exts[e++] = SegExtent{x.start, x.n};
+    j.ext_end = (uint32_t)e;
+    j.ts_base = ts_at;
+    j.ts_cap = pow2_ge(std::max<uint64_t>(v.n_frames, 1));
+    j.seg_base = seg_at;
+    j.duration = durations[i];
+    (*seg_base_out)[i] = seg_at;
+    ts_at += j.ts_cap;
+    seg_at += std::max<uint64_t>(v.n_frames, 1);
+    c->h_jobs[i] = j;
+  }
+  cudaStream_t st = c->main_stream;
+  CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice, st));
+  if (n_ext) CU(cudaMemcpyAsync(c->d_exts, c->h_exts, sizeof(SegExtent) * n_ext, cudaMemcpyHostToDevice, st));
+  c->stats.h2d_bytes += sizeof(SegJob) * n_videos + sizeof(SegExtent) * n_ext;
+  SegArgs a{};
+  a.jobs = c->d_jobs;
+  a.extents = c->d_exts;
+  a.pts = c->d_pts;
+  a.flags = c->d_flags;
+  a.ts_a = c->d_ts_a;
+  a.ts_b = c->d_ts_b;
+  a.segs = c->d_segs;
+  a.results = c->d_res;
+  a.max_gap = c->params.max_gap_sec;
+  a.padding = c->params.padding_sec;
+  a.min_savings_pct = c->params.min_savings_pct;
+  EvPair ev{};
+  if (c->profiling) {
+    ev = get_events(c, 1);
+    cudaEventRecord(ev.a, st);
+  }
+  CU(segments_launch(a, n_videos, st));
+  if (c->profiling) {
+    cudaEventRecord(ev.b, st);
+    c->ev_pending.push_back(ev);
+  }
+  c->stats.segment_launches += 1;
+  CU(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(mscan_video_result) * n_videos, cudaMemcpyDeviceToHost, st));
+  c->stats.d2h_bytes += sizeof(mscan_video_result) * n_videos;
+  CU(cudaStreamSynchronize(st));
+  return MSCAN_OK;
+}
+
+static int segments_impl(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
+                         mscan_segment* out, uint64_t cap, uint64_t* seg_off_out, mscan_video_result* res_out,
+                         bool job_semantics) {
+  if (!c || (n_videos && (!ids || !durations))) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  if (n_videos == 0) {
+    if (seg_off_out) seg_off_out[0] = 0;
+    return MSCAN_OK;
+  }
+  std::vector<uint64_t> seg_base;
+  int rc = run_segments_locked(c, n_videos, ids, durations, &seg_base);
+  if (rc) return rc;
+  uint64_t at = 0;
+  bool overflow = false;
+  for (uint32_t i = 0; i < n_videos; ++i) {
+    const mscan_video_result& r = c->h_res[i];
+    if (res_out) res_out[i] = r;
+    if (seg_off_out) seg_off_out[i] = at;
+    uint64_t n = r.n_segments;
+    const bool full_copy = job_semantics && r.decision == MSCAN_FULL_COPY;
+    if (job_semantics && r.decision == MSCAN_NO_MOTION) n = 0;
+    if (full_copy) n = 1;
+    if (at + n > cap || (!out && n)) {
+      overflow = true;
+    } else if (full_copy) {
+      out[at] = mscan_segment{0.0, durations[i]};  // pipeline.cpp:386-387
+    } else if (n) {
+      CU(cudaMemcpyAsync(out + at, c->d_segs + seg_base[i], sizeof(mscan_segment) * n, cudaMemcpyDeviceToHost, c->main_stream));
+      c->stats.d2h_bytes += sizeof(mscan_segment) * n;
+    }
+    at += n;
+  }
+  if (seg_off_out) seg_off_out[n_videos] = at;
+  CU(cudaStreamSynchronize(c->main_stream));
+  if (overflow) return fail(c, MSCAN_ERR_CAPACITY, "segment buffer too small: need %llu", (unsigned long long)at);
+  return MSCAN_OK;
+}
+
+int mscan_segments_batch(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
+                         mscan_segment* out, uint64_t cap, uint64_t* seg_off_out, mscan_video_result* res_out) {
+  return segments_impl(c, n_videos, ids, durations, out, cap, seg_off_out, res_out, true);
+}
+
+int mscan_segments(mscan_ctx* c, uint32_t video_id, double duration, mscan_segment* out, uint32_t cap, uint32_t* n_out,
+                   mscan_video_result* res_out) {
+  uint64_t off[2] = {0, 0};
+  int rc = segments_impl(c, 1, &video_id, &duration, out, cap, off, res_out, true);
+  if (n_out) *n_out = (uint32_t)off[1];
+  return rc;
+}
+
+int mscan_motion_segments(mscan_ctx* c, uint32_t video_id, double duration, mscan_segment* out, uint32_t cap,
+                          uint32_t* n_out, mscan_video_result* res_out) {
+  uint64_t off[2] = {0, 0};
+  int rc = segments_impl(c, 1, &video_id, &duration, out, cap, off, res_out, false);
+  if (n_out) *n_out = (uint32_t)off[1];
+  return rc;
+}
+
+int mscan_video_close(mscan_ctx* c, uint32_t video_id) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  c->videos.erase(it);
+  if (c->videos.empty()) {
+    // the log holds nothing live any more: rewind it once in-flight scans are done
+    CU(cudaSetDevice(c->device));
+    int rc = sync_scans_locked(c);
+    if (rc) return rc;
+    c->log_head = 0;
+  }
+  return MSCAN_OK;
+}
+
+int mscan_host_alloc(mscan_ctx* c, size_t bytes, void** p) {
+  if (!c || !p) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  if (cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, MSCAN_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+  }
+  return MSCAN_OK;
+}
+
+int mscan_host_free(mscan_ctx* c, void* p) {
+  if (!c) return MSCAN_ERR_INVALID;
+  if (p) CU(cudaFreeHost(p));
+  return MSCAN_OK;
+}
+
+// ---- device-resident path -----------------------------------------------------------------------
+int mscan_dev_alloc(mscan_ctx* c, size_t bytes, void** d) {
+  if (!c || !d) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  if (cudaMalloc(d, bytes ? bytes : 1) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, MSCAN_ERR_NOMEM, "cudaMalloc(%zu) failed", bytes);
+  }
+  return MSCAN_OK;
+}
+
+int mscan_dev_free(mscan_ctx* c, void* d) {
+  if (!c) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  if (d) CU(cudaFree(d));
+  return MSCAN_OK;
+}
+
+int mscan_memcpy_h2d(mscan_ctx* c, void* d, const void* h, size_t bytes) {
+  if (!c) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice));
+  return MSCAN_OK;
+}
+
+int mscan_memcpy_d2h(mscan_ctx* c, void* h, const void* d, size_t bytes) {
+  if (!c) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost));
+  return MSCAN_OK;
+}
+
+int mscan_offsets_from_counts(mscan_ctx* c, const uint32_t* d_cnt, uint32_t n, uint64_t* d_off, void* stream) {
+  if (!c || !d_off || (n && !d_cnt)) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->main_stream;
+  CU(offsets_launch(d_cnt, n, d_off, nullptr, st));
+  c->stats.aux_launches += 1;
+  return MSCAN_OK;
+}
+
+int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_rec_off, const uint32_t* d_frame_geom,
+                      const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames, uint8_t* d_flags,
+                      uint32_t* d_counts, void* stream) {
+  if (!c || !d_rec_off || !geoms || n_geoms == 0 || !d_flags || !d_counts) return MSCAN_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(d_recs) & 15u) != 0) return fail(c, MSCAN_ERR_INVALID, "d_recs must be 16-byte aligned");
+  if (n_geoms > kMaxGeoms) return fail(c, MSCAN_ERR_CAPACITY, "too many geometries");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->main_stream;
+  std::vector<DevGeom> dg(n_geoms);
+  uint32_t cells = 0, words = 0;
+  for (uint32_t i = 0; i < n_geoms; ++i) {
+    if (!geom_ok(geoms[i])) return fail(c, MSCAN_ERR_INVALID, "bad geometry %u", i);
+    dg[i] = to_dev_geom(geoms[i]);
+    uint32_t ce, wo;
+    geom_need(dg[i], &ce, &wo);
+    cells = std::max(cells, ce);
+    words = std::max(words, wo);
+  }
+  ScanPlan plan;
+  if (!scan_plan(cells, words, c->smem_optin, &plan))
+    return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells does not fit shared memory", cells);
+  if (n_geoms > c->user_geoms_cap) {
+    cudaFree(c->d_user_geoms);
+    c->user_geoms_cap = 0;
+    CU(cudaMalloc((void**)&c->d_user_geoms, sizeof(DevGeom) * std::max(n_geoms, 16u)));
+    c->user_geoms_cap = std::max(n_geoms, 16u);
+  }
+  // pageable source: the copy is staged by the runtime before the call returns
+  CU(cudaMemcpyAsync(c->d_user_geoms, dg.data(), sizeof(DevGeom) * n_geoms, cudaMemcpyHostToDevice, st));
+  ScanArgs a = base_args(c);
+  a.recs = reinterpret_cast<const uint8_t*>(d_recs);
+  a.rec_off = d_rec_off;
+  a.frame_geom = d_frame_geom;
+  a.geoms = c->d_user_geoms;
+  a.flags = d_flags;
+  a.counts = d_counts;
+  a.n_frames = n_frames;
+  a.stages = plan.stages;
+  a.max_cells = cells;
+  a.max_bit_words = words;
+  return run_scan(c, a, plan, st, 0);
+}
+
+int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_video_off, const double* h_durations,
+                          const double* d_pts, const uint8_t* d_flags, mscan_segment* d_segments,
+                          mscan_video_result* d_results, void* stream) {
+  if (!c || !h_video_off || !h_durations || !d_pts || !d_flags || !d_segments || !d_results) return MSCAN_ERR_INVALID;
+  if (n_videos == 0) return MSCAN_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->main_stream;
+  // job tables live in pinned memory that must not be rewritten while a previous launch reads it
+  CU(cudaStreamSynchronize(st));
+  uint64_t ts_total = 0;
+  for (uint32_t v = 0; v < n_videos; ++v) {
+    if (h_video_off[v + 1] < h_video_off[v]) return fail(c, MSCAN_ERR_INVALID, "video offsets must be non-decreasing");
+    ts_total += pow2_ge(std::max<uint64_t>(h_video_off[v + 1] - h_video_off[v], 1));
+  }
+  if (n_videos > c->job_cap) {
+    if (c->h_jobs) cudaFreeHost(c->h_jobs);
+    if (c->h_res) cudaFreeHost(c->h_res);
+    cudaFree(c->d_jobs);
+    cudaFree(c->d_res);
+    c->job_cap = 0;
+    const uint32_t n = std::max(n_videos, 64u);
+    CU(cudaHostAlloc((void**)&c->h_jobs, sizeof(SegJob) * n, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&c->h_res, sizeof(mscan_video_result) * n, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&c->d_jobs, sizeof(SegJob) * n));
+    CU(cudaMalloc((void**)&c->d_res, sizeof(mscan_video_result) * n));
+    c->job_cap = n;
+  }
+  if (n_videos > c->ext_cap) {
+    if (c->h_exts) cudaFreeHost(c->h_exts);
+    cudaFree(c->d_exts);
+    c->ext_cap = 0;
+    const uint32_t n = std::max(n_videos, 256u);
+    CU(cudaHostAlloc((void**)&c->h_exts, sizeof(SegExtent) * n, cudaHostAllocDefault));
+    CU(cudaMalloc((void**)&c->d_exts, sizeof(SegExtent) * n));
+    c->ext_cap = n;
+  }
+  {
+    uint64_t cap = c->ts_cap;
+    int rc = grow(c, &c->d_ts_a, &cap, ts_total);
+    if (rc) return rc;
+    uint64_t cap_b = c->ts_cap;
+    rc = grow(c, &c->d_ts_b, &cap_b, ts_total);
+    if (rc) return rc;
+    c->ts_cap = std::min(cap, cap_b);
+  }
+  uint64_t ts_at = 0;
+  for (uint32_t v = 0; v < n_videos; ++v) {
+    const uint64_t n = h_video_off[v + 1] - h_video_off[v];
+    c->h_exts[v] = SegExtent{h_video_off[v], n};
+    SegJob j{};
+    j.ext_begin = v;
+    j.ext_end = v + 1;
+    j.ts_base = ts_at;
+    j.ts_cap = pow2_ge(std::max<uint64_t>(n, 1));
+    j.seg_base = h_video_off[v];
+    j.duration = h_durations[v];
+    ts_at += j.ts_cap;
+    c->h_jobs[v] = j;
+  }
+  CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->d_exts, c->h_exts, sizeof(SegExtent) * n_videos, cudaMemcpyHostToDevice, st));
+  SegArgs a{};
+  a.jobs = c->d_jobs;
+  a.extents = c->d_exts;
+  a.pts = d_pts;
+  a.flags = d_flags;
+  a.ts_a = c->d_ts_a;
+  a.ts_b = c->d_ts_b;
+  a.segs = d_segments;
+  a.results = d_results;
+  a.max_gap = c->params.max_gap_sec;
+  a.padding = c->params.padding_sec;
+  a.min_savings_pct = c->params.min_savings_pct;
+  EvPair ev{};
+  if (c->profiling) {
+    ev = get_events(c, 1);
+    cudaEventRecord(ev.a, st);
+  }
+  CU(segments_launch(a, n_videos, st));
+  if (c->profiling) {
+    cudaEventRecord(ev.b, st);
+    c->ev_pending.push_back(ev);
+  }
+  c->stats.segment_launches += 1;
+  return MSCAN_OK;
+}
+
+// ---- measurement harness ------------------------------------------------------------------------
+int mscan_synth_counts(mscan_ctx* c, const mvgen_spec* spec, uint64_t frame0, uint32_t n_frames, uint32_t* d_cnt,
+                       void* stream) {
+  if (!c || !spec || !d_cnt) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(synth_counts_launch(*spec, frame0, n_frames, d_cnt, stream ? (cudaStream_t)stream : c->main_stream));
+  c->stats.aux_launches += 1;
+  return MSCAN_OK;
+}
+
+int mscan_synth_fill(mscan_ctx* c, const mvgen_spec* spec, uint64_t frame0, uint32_t n_frames, const uint64_t* d_off,
+                     mscan_mv* d_recs, double* d_pts, void* stream) {
+  if (!c || !spec || !d_off || !d_recs) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(synth_fill_launch(*spec, frame0, n_frames, d_off, d_recs, d_pts, stream ? (cudaStream_t)stream : c->main_stream));
+  c->stats.aux_launches += 1;
+  return MSCAN_OK;
+}
+
+}  // extern "C"
