@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py — motion-scan hot path on B200: MV records/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU path on the box's host cores
+
+Workload (config.workload): BASELINE.json configs[4] — a decode-free synthetic AVMotionVector stream
+of ~10^9 native 40-byte records per GPU (1080p30 CCTV mix cut into 10-minute videos), generated on the
+device by the deterministic generator of include/mvgen_core.h. One step = K-A over every frame of the
+stream + K-C over every video. Weak scaling: every rank owns a stream of the same size (seed + rank);
+videos are independent, so there is no collective on the data path (torch.distributed only provides
+the barrier and the max-over-ranks of the timings).
+
+Reported on one JSON line: `value` (device-resident records/s, whole job), `roofline` (K-A's
+algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs), `e2e` (same metric
+through the host-facing C ABI with pinned HOST buffers: H2D of every record + D2H of the results
+inside the timed region), `cpu_baseline` (the oracle port on this box's host cores, bounded sample),
+`clocks`, `gpu_launches`.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT / "motion-estimated-video-trimmer_b200"))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "mv_records_per_s"
+UNIT = "records/s"
+REC_BYTES = 40
+FRAME_BYTES = 17  # 4 B count + 8 B pts in, 1 B flag + 4 B count out
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------ clocks ------
+class ClockSampler:
+    """Samples SM clock + throttle reasons during the timed region (pynvml, else nvidia-smi)."""
+
+    REASONS = {
+        0x4: "sw_power_cap",
+        0x8: "hw_slowdown",
+        0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown",
+    }
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._h is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {
+            "sm_mhz": float(np.median(self.samples)),
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+# --------------------------------------------------------------------------------- CPU legs -------
+def host_sample(ms, spec, n_frames, threads):
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n_frames, n_threads=threads)
+    return cnt, off, recs, pts
+
+
+def cpu_scan_rate(ms, orc, params, spec, off, recs, pts, threads, min_seconds):
+    """Oracle port (check_frame restatement, full-count variant + tail) over the sample; records/s."""
+    gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
+    cfg = orc.make_cfg(params, gw, gh, m)
+    n_rec = int(off[-1])
+    passes, t_total = 0, 0.0
+    while True:
+        t0 = time.perf_counter()
+        flags, _ = orc.scan_frames(cfg, recs, off, early_exit=False, threads=threads)
+        fpv = spec.frames_per_video or len(pts)
+        for a in range(0, len(pts), fpv):
+            b = min(len(pts), a + fpv)
+            orc.video_tail(pts[a:b], flags[a:b], (b - a) / spec.fps, params.max_gap_sec, params.padding_sec, params.min_savings_pct)
+        t_total += time.perf_counter() - t0
+        passes += 1
+        if t_total >= min_seconds or passes >= 50:
+            break
+    return n_rec * passes / t_total, passes, t_total
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores, all threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import motionscan as ms
+    import oracle_lib as orc
+
+    threads = os.cpu_count() or 1
+    params = ms.shipped_env_params()
+    spec = ms.synth_preset(4, 5)
+    n_frames = args.cpu_frames
+    cnt, off, recs, pts = host_sample(ms, spec, n_frames, threads)
+    n_rec = int(off[-1])
+    gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
+    cfg = orc.make_cfg(params, gw, gh, m)
+
+    def step():
+        flags, _ = orc.scan_frames(cfg, recs, off, early_exit=True, threads=threads)  # reference semantics
+        fpv = spec.frames_per_video or n_frames
+        for a in range(0, n_frames, fpv):
+            b = min(n_frames, a + fpv)
+            orc.video_tail(pts[a:b], flags[a:b], (b - a) / spec.fps, params.max_gap_sec, params.padding_sec, params.min_savings_pct)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n_rec * args.steps / dt
+    kind = "port"
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int32",
+        "data": "synthetic",
+        "config": workload_config(spec, n_frames, n_rec, "host"),
+        "frames_per_s": n_frames * args.steps / dt,
+        "cpu_baseline": {
+            "value": value,
+            "unit": UNIT,
+            "cores": threads,
+            "kind": kind,
+            "sample": f"{n_frames} frames / {n_rec} records of the same stream per step, early-exit (reference) semantics",
+        },
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(spec, n_frames, n_rec, where):
+    return {
+        "workload": "mvstream_1e9: decode-free synthetic AVMotionVector stream (BASELINE.json configs[4]), "
+        "1080p30 CCTV mix cut into 10-min videos, native 40-B records",
+        "resident": where,
+        "frames": int(n_frames),
+        "records": int(n_rec),
+        "frames_per_video": int(spec.frames_per_video),
+        "params": "config/motion_trim.env: MV_THRESHOLD_SQ=4 VECTORS_NEEDED=4 CLUSTERS_NEEDED=2 VERTICAL_MASK=0.05 MAX_GAP_SEC=5 PADDING_SEC=0.5 MIN_SAVINGS_PCT=5",
+        "l2": "inputs larger than L2 (no flush needed)",
+    }
+
+
+# ---------------------------------------------------------------------------------- GPU arm -------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    import motionscan as ms
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the motion-scan path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    params = ms.shipped_env_params()
+    ctx = ms.Context(local, params, max_log_frames=1 << 20, slab_bytes=args.slab_mb << 20)
+    stream = torch.cuda.Stream()
+    sh = stream.cuda_stream
+
+    # ---- build the device-resident stream ---------------------------------------------------------
+    spec = ms.synth_preset(4, 5 + rank)
+    probe = 4096
+    d_probe = ctx.dev_alloc(4 * probe)
+    ctx.synth_counts(spec, 0, probe, d_probe, sh)
+    stream.synchronize()
+    pc = np.zeros(probe, np.uint32)
+    ctx.d2h(pc, d_probe)
+    ctx.dev_free(d_probe)
+    n_frames = int(np.ceil(args.records / max(pc.mean(), 1.0)))
+    d_cnt = ctx.dev_alloc(4 * n_frames)
+    d_off = ctx.dev_alloc(8 * (n_frames + 1))
+    ctx.synth_counts(spec, 0, n_frames, d_cnt, sh)
+    ctx.offsets_from_counts(d_cnt, n_frames, d_off, sh)
+    stream.synchronize()
+    off = np.zeros(n_frames + 1, np.uint64)
+    ctx.d2h(off, d_off)
+    n_rec = int(off[-1])
+    d_recs = ctx.dev_alloc(REC_BYTES * n_rec + 256)
+    d_pts = ctx.dev_alloc(8 * n_frames)
+    d_flags = ctx.dev_alloc(n_frames)
+    d_counts = ctx.dev_alloc(4 * n_frames)
+    d_segs = ctx.dev_alloc(16 * n_frames)
+    ctx.synth_fill(spec, 0, n_frames, d_off, d_recs, d_pts, sh)
+    stream.synchronize()
+    fpv = spec.frames_per_video
+    voff = np.array(list(range(0, n_frames, fpv)) + [n_frames], dtype=np.uint64)
+    n_videos = len(voff) - 1
+    durations = np.diff(voff).astype(np.float64) / spec.fps
+    d_res = ctx.dev_alloc(40 * n_videos)
+    geom = ms.geometry_from_dims(params, spec.width, spec.height)
+
+    def step():
+        ctx.scan_device(d_recs, d_off, None, [geom], n_frames, d_flags, d_counts, sh)
+        ctx.segments_device(voff, durations, d_pts, d_flags, d_segs, d_res, sh)
+
+    for _ in range(args.warmup):
+        step()
+    stream.synchronize()
+    ctx.reset_stats()
+    ctx.set_profiling(True)
+    sampler = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    stream.synchronize()
+    torch.cuda.synchronize()
+    sampler.stop()
+    barrier()
+    ms_total = allmax(e0.elapsed_time(e1))
+    st = ctx.stats()
+    ctx.set_profiling(False)
+    ka_ms = st.scan_ms / max(st.scan_launches, 1)
+    kc_ms = st.segment_ms / max(st.segment_launches, 1)
+    launches = int(st.scan_launches + st.segment_launches)
+    total_rec = allsum(float(n_rec))
+    total_frames = allsum(float(n_frames))
+    value = total_rec * args.steps / (ms_total * 1e-3)
+
+    # sanity on the results of the last step (not timed): flags must be a mix, every video decided
+    flags = np.zeros(n_frames, np.uint8)
+    res = np.zeros(n_videos, ms.RESULT_DTYPE)
+    ctx.d2h(flags, d_flags)
+    ctx.d2h(res, d_res)
+
+    # ---- e2e: host-fed through the C ABI ------------------------------------------------------------
+    e2e_frames = min(args.e2e_frames, n_frames)
+    e_rec = int(off[e2e_frames])
+    h_recs = ctx.pinned_array(e_rec, ms.MV_DTYPE)
+    h_pts = ctx.pinned_array(e2e_frames, np.float64)
+    h_cnt = np.diff(off[: e2e_frames + 1]).astype(np.uint32)
+    ctx.d2h(h_recs, d_recs)
+    ctx.d2h(h_pts, d_pts)
+    e_voff = list(range(0, e2e_frames, fpv)) + [e2e_frames]
+
+    def e2e_step():
+        vids = []
+        for v in range(len(e_voff) - 1):
+            a, b = e_voff[v], e_voff[v + 1]
+            ctx.video_open(v, spec.width, spec.height)
+            ctx.submit_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_recs.ctypes.data + REC_BYTES * int(off[a]))
+            vids.append(v)
+        out = [ctx.collect(v) for v in vids]
+        segs = ctx.segments_batch(vids, [(e_voff[v + 1] - e_voff[v]) / spec.fps for v in vids])
+        for v in vids:
+            ctx.video_close(v)
+        return out, segs
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        e2e_out = e2e_step()
+    ctx.sync()
+    ctx.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_out = e2e_step()
+    ctx.sync()
+    e2e_dt = allmax(time.perf_counter() - t0)
+    est = ctx.stats()
+    e2e_value = allsum(float(e_rec)) * e2e_steps / e2e_dt
+    e2e_launches = int(est.scan_launches + est.segment_launches)
+    # the host-fed results must equal the device-resident ones for the same frames
+    e_flags = np.concatenate([o[0] for o in e2e_out[0]])
+    e2e_ok = bool(np.array_equal(e_flags, flags[:e2e_frames]))
+
+    # ---- CPU baseline on rank 0, N=1 only ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as orc
+
+        threads = os.cpu_count() or 1
+        c_frames = min(args.cpu_frames, e2e_frames)
+        c_off = off[: c_frames + 1]
+        c_recs = h_recs[: int(c_off[-1])]
+        c_pts = h_pts[:c_frames]
+        v1, p1, t1 = cpu_scan_rate(ms, orc, params, spec, c_off, c_recs, c_pts, 1, args.cpu_seconds / 2)
+        vn, pn, tn = cpu_scan_rate(ms, orc, params, spec, c_off, c_recs, c_pts, threads, args.cpu_seconds / 2)
+        # parity of the sample while we are here: oracle flags == GPU flags
+        gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
+        of, _ = orc.scan_frames(orc.make_cfg(params, gw, gh, m), c_recs, c_off, threads=threads)
+        cpu = {
+            "value": vn,
+            "unit": UNIT,
+            "cores": threads,
+            "kind": "port",
+            "value_1thread": v1,
+            "sample": f"first {c_frames} frames / {int(c_off[-1])} records of the stream, full-count variant + tail, "
+            f"{pn} passes in {tn:.1f} s ({threads} threads), {p1} passes in {t1:.1f} s (1 thread)",
+            "parity_with_gpu": bool(np.array_equal(of, flags[:c_frames])),
+        }
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        ka_bytes = REC_BYTES * n_rec + FRAME_BYTES * n_frames
+        achieved = ka_bytes / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
+        line = {
+            "metric": METRIC,
+            "value": value,
+            "unit": UNIT,
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "int32",
+            "data": "synthetic",
+            "config": workload_config(spec, n_frames, n_rec, "hbm"),
+            "frames_per_s": total_frames * args.steps / (ms_total * 1e-3),
+            "roofline": {
+                "bound": "hbm",
+                "kernel": "ka_scan_kernel",
+                "achieved": achieved,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": peak_src,
+                "bytes_per_launch": ka_bytes,
+                "ms_per_launch": ka_ms,
+                "kc_ms_per_launch": kc_ms,
+            },
+            "e2e": {
+                "value": e2e_value,
+                "unit": UNIT,
+                "h2d_bytes_per_step": int(est.h2d_bytes // e2e_steps),
+                "d2h_bytes_per_step": int(est.d2h_bytes // e2e_steps),
+                "steps": e2e_steps,
+                "frames": e2e_frames,
+                "records": e_rec,
+                "h2d_gbs": est.h2d_bytes / e2e_dt / 1e9,
+                "launches": e2e_launches,
+                "matches_device_resident": e2e_ok,
+                "how": "mscan_video_open/submit (pinned host records DMA'd in place)/collect/segments_batch/close per step",
+            },
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(),
+            "gpu_launches": launches,
+            "results": {
+                "active_frames": int(flags.sum()),
+                "videos": int(n_videos),
+                "cut": int((res["decision"] == ms.CUT).sum()),
+                "full_copy": int((res["decision"] == ms.FULL_COPY).sum()),
+                "no_motion": int((res["decision"] == ms.NO_MOTION).sum()),
+                "segments": int(res["n_segments"].sum()),
+            },
+        }
+        print(json.dumps(line), flush=True)
+    ctx.host_free(h_recs.ctypes.data)
+    ctx.host_free(h_pts.ctypes.data)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--records", type=float, default=1e9, help="records per GPU in the device-resident stream")
+    ap.add_argument("--e2e-frames", type=int, default=9000, help="frames of the host-resident e2e sample (~4 GB)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-frames", type=int, default=3000, help="frames of the CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=16.0)
+    ap.add_argument("--slab-mb", type=int, default=256)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -119,6 +119,9 @@ struct mscan_ctx {
   // geometry staging for the device API
   DevGeom* d_user_geoms = nullptr;
   uint32_t user_geoms_cap = 0;
+  std::vector<DevGeom> user_geoms_cached;  // what d_user_geoms currently holds
+  // last job table uploaded by mscan_segments_device (re-used when unchanged: no sync, no copy)
+  std::vector<SegJob> dev_jobs_cached;
 
   mscan_stats stats{};
   bool profiling = false;
@@ -813,6 +816,7 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
     rc = grow(c, &c->d_segs, &c->seg_cap, seg_total);
     if (rc) return rc;
   }
+  c->dev_jobs_cached.clear();
   seg_base_out->resize(n_videos);
   uint64_t e = 0, ts_at = 0, seg_at = 0;
   for (uint32_t i = 0; i < n_videos; ++i) {
@@ -1022,11 +1026,17 @@ int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_re
   if (n_geoms > c->user_geoms_cap) {
     cudaFree(c->d_user_geoms);
     c->user_geoms_cap = 0;
+    c->user_geoms_cached.clear();
     CU(cudaMalloc((void**)&c->d_user_geoms, sizeof(DevGeom) * std::max(n_geoms, 16u)));
     c->user_geoms_cap = std::max(n_geoms, 16u);
   }
-  // pageable source: the copy is staged by the runtime before the call returns
-  CU(cudaMemcpyAsync(c->d_user_geoms, dg.data(), sizeof(DevGeom) * n_geoms, cudaMemcpyHostToDevice, st));
+  // upload only when the table changed: a pageable-source copy would serialise the stream
+  if (c->user_geoms_cached.size() != n_geoms ||
+      std::memcmp(c->user_geoms_cached.data(), dg.data(), sizeof(DevGeom) * n_geoms) != 0) {
+    CU(cudaStreamSynchronize(st));
+    CU(cudaMemcpy(c->d_user_geoms, dg.data(), sizeof(DevGeom) * n_geoms, cudaMemcpyHostToDevice));
+    c->user_geoms_cached = dg;
+  }
   ScanArgs a = base_args(c);
   a.recs = reinterpret_cast<const uint8_t*>(d_recs);
   a.rec_off = d_rec_off;
@@ -1049,60 +1059,66 @@ int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_vid
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->main_stream;
-  // job tables live in pinned memory that must not be rewritten while a previous launch reads it
-  CU(cudaStreamSynchronize(st));
+  std::vector<SegJob> jobs(n_videos);
   uint64_t ts_total = 0;
   for (uint32_t v = 0; v < n_videos; ++v) {
     if (h_video_off[v + 1] < h_video_off[v]) return fail(c, MSCAN_ERR_INVALID, "video offsets must be non-decreasing");
-    ts_total += pow2_ge(std::max<uint64_t>(h_video_off[v + 1] - h_video_off[v], 1));
-  }
-  if (n_videos > c->job_cap) {
-    if (c->h_jobs) cudaFreeHost(c->h_jobs);
-    if (c->h_res) cudaFreeHost(c->h_res);
-    cudaFree(c->d_jobs);
-    cudaFree(c->d_res);
-    c->job_cap = 0;
-    const uint32_t n = std::max(n_videos, 64u);
-    CU(cudaHostAlloc((void**)&c->h_jobs, sizeof(SegJob) * n, cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&c->h_res, sizeof(mscan_video_result) * n, cudaHostAllocDefault));
-    CU(cudaMalloc((void**)&c->d_jobs, sizeof(SegJob) * n));
-    CU(cudaMalloc((void**)&c->d_res, sizeof(mscan_video_result) * n));
-    c->job_cap = n;
-  }
-  if (n_videos > c->ext_cap) {
-    if (c->h_exts) cudaFreeHost(c->h_exts);
-    cudaFree(c->d_exts);
-    c->ext_cap = 0;
-    const uint32_t n = std::max(n_videos, 256u);
-    CU(cudaHostAlloc((void**)&c->h_exts, sizeof(SegExtent) * n, cudaHostAllocDefault));
-    CU(cudaMalloc((void**)&c->d_exts, sizeof(SegExtent) * n));
-    c->ext_cap = n;
-  }
-  {
-    uint64_t cap = c->ts_cap;
-    int rc = grow(c, &c->d_ts_a, &cap, ts_total);
-    if (rc) return rc;
-    uint64_t cap_b = c->ts_cap;
-    rc = grow(c, &c->d_ts_b, &cap_b, ts_total);
-    if (rc) return rc;
-    c->ts_cap = std::min(cap, cap_b);
-  }
-  uint64_t ts_at = 0;
-  for (uint32_t v = 0; v < n_videos; ++v) {
     const uint64_t n = h_video_off[v + 1] - h_video_off[v];
-    c->h_exts[v] = SegExtent{h_video_off[v], n};
     SegJob j{};
     j.ext_begin = v;
     j.ext_end = v + 1;
-    j.ts_base = ts_at;
+    j.ts_base = ts_total;
     j.ts_cap = pow2_ge(std::max<uint64_t>(n, 1));
     j.seg_base = h_video_off[v];
     j.duration = h_durations[v];
-    ts_at += j.ts_cap;
-    c->h_jobs[v] = j;
+    ts_total += j.ts_cap;
+    jobs[v] = j;
   }
-  CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c->d_exts, c->h_exts, sizeof(SegExtent) * n_videos, cudaMemcpyHostToDevice, st));
+  const bool same = c->dev_jobs_cached.size() == n_videos && ts_total <= c->ts_cap &&
+                    std::memcmp(c->dev_jobs_cached.data(), jobs.data(), sizeof(SegJob) * n_videos) == 0;
+  if (!same) {
+    // tables and scratch may still be read by an earlier launch: drain before touching them
+    CU(cudaDeviceSynchronize());
+    c->dev_jobs_cached.clear();
+    if (n_videos > c->job_cap) {
+      if (c->h_jobs) cudaFreeHost(c->h_jobs);
+      if (c->h_res) cudaFreeHost(c->h_res);
+      cudaFree(c->d_jobs);
+      cudaFree(c->d_res);
+      c->job_cap = 0;
+      const uint32_t n = std::max(n_videos, 64u);
+      CU(cudaHostAlloc((void**)&c->h_jobs, sizeof(SegJob) * n, cudaHostAllocDefault));
+      CU(cudaHostAlloc((void**)&c->h_res, sizeof(mscan_video_result) * n, cudaHostAllocDefault));
+      CU(cudaMalloc((void**)&c->d_jobs, sizeof(SegJob) * n));
+      CU(cudaMalloc((void**)&c->d_res, sizeof(mscan_video_result) * n));
+      c->job_cap = n;
+    }
+    if (n_videos > c->ext_cap) {
+      if (c->h_exts) cudaFreeHost(c->h_exts);
+      cudaFree(c->d_exts);
+      c->ext_cap = 0;
+      const uint32_t n = std::max(n_videos, 256u);
+      CU(cudaHostAlloc((void**)&c->h_exts, sizeof(SegExtent) * n, cudaHostAllocDefault));
+      CU(cudaMalloc((void**)&c->d_exts, sizeof(SegExtent) * n));
+      c->ext_cap = n;
+    }
+    {
+      uint64_t cap = c->ts_cap;
+      int rc = grow(c, &c->d_ts_a, &cap, ts_total);
+      if (rc) return rc;
+      uint64_t cap_b = c->ts_cap;
+      rc = grow(c, &c->d_ts_b, &cap_b, ts_total);
+      if (rc) return rc;
+      c->ts_cap = std::min(cap, cap_b);
+    }
+    for (uint32_t v = 0; v < n_videos; ++v) {
+      c->h_exts[v] = SegExtent{h_video_off[v], h_video_off[v + 1] - h_video_off[v]};
+      c->h_jobs[v] = jobs[v];
+    }
+    CU(cudaMemcpy(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_exts, c->h_exts, sizeof(SegExtent) * n_videos, cudaMemcpyHostToDevice));
+    c->dev_jobs_cached = jobs;
+  }
   SegArgs a{};
   a.jobs = c->d_jobs;
   a.extents = c->d_exts;
