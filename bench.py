@@ -14,7 +14,8 @@ the barrier and the max-over-ranks of the timings).
 Reported on one JSON line: `value` (device-resident records/s, whole job), `roofline` (K-A's
 algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs), `e2e` (same metric
 through the host-facing C ABI with pinned HOST buffers: H2D of every record + D2H of the results
-inside the timed region), `cpu_baseline` (the oracle port on this box's host cores, bounded sample),
+inside the timed region), `cpu_baseline` (the reference built as oracle/_ref, else the oracle port, on this
+box's host cores, bounded sample),
 `clocks`, `gpu_launches`.
 """
 from __future__ import annotations
@@ -48,6 +49,20 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(n_rec, n_frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one K-A launch from the committed `ncu --set full`
+    capture (profiles/*ka_traffic.json) — only when that capture was taken on this exact workload."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("*ka_traffic.json")):
+        try:
+            d = json.loads(f.read_text())
+            if int(d["records"]) == int(n_rec) and int(d["frames"]) == int(n_frames):
+                best = (float(d["traffic"]), f.name)
+        except Exception:
+            continue
+    return best
 
 
 # ------------------------------------------------------------------------------------ clocks ------
@@ -114,29 +129,80 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- CPU legs -------
-def host_sample(ms, spec, n_frames, threads):
-    cnt, off, recs, pts = ms.synth_host(spec, 0, n_frames, n_threads=threads)
-    return cnt, off, recs, pts
+def cpu_leg(ms, params, spec, n_frames, threads, passes, warmup, sample_data=None):
+    """The CPU implementation of the path on this box's host cores, on the first n_frames frames of the
+    stream. kind "reference": oracle/_ref/ref_scan — the reference's own motion_scanner.cpp / pipeline.cpp
+    (built in the build container against the fake-libav shim) — `threads` MotionScanner instances over
+    disjoint time ranges through the public scan_range(), timed by the reference's OWN analyze timer
+    around check_frame (motion_scanner.cpp:375-380); the step time is the slowest thread's analyze time
+    (decode stand-in excluded). kind "port": the oracle restatement, early-exit semantics, pthreads."""
+    import mvs_io
+    import oracle_lib as orc
+    import ref_runner
 
-
-def cpu_scan_rate(ms, orc, params, spec, off, recs, pts, threads, min_seconds):
-    """Oracle port (check_frame restatement, full-count variant + tail) over the sample; records/s."""
-    gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
-    cfg = orc.make_cfg(params, gw, gh, m)
+    if sample_data is None:
+        cnt, off, recs, pts = ms.synth_host(spec, 0, n_frames, n_threads=threads)
+    else:
+        cnt, off, recs, pts = sample_data
     n_rec = int(off[-1])
-    passes, t_total = 0, 0.0
-    while True:
+    out = {"unit": UNIT, "cores": threads}
+    if ref_runner.available():
+        import tempfile
+
+        d = "/dev/shm" if os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+        path = os.path.join(d, f"mscan_bench_{os.getpid()}.mvs")
+        try:
+            mvs_io.write_mvs(path, spec.width, spec.height, int(spec.fps), 1, np.arange(n_frames), cnt, recs)
+            dur = n_frames / spec.fps
+            chunk = max(1.0, dur / (2 * threads))  # CHUNK_DURATION_SEC: at least 2 chunks per worker thread
+            r = ref_runner.run(path, params, threads=threads, passes=passes, warmup=warmup, chunk_sec=chunk)
+            r1 = ref_runner.run(path, params, threads=1, passes=1, warmup=0, chunk_sec=chunk) if threads > 1 else r
+        finally:
+            if os.path.exists(path):
+                os.unlink(path)
+        hot_s = r["par_analyze_max_us"] * 1e-6
+        out.update(
+            kind="reference",
+            value=n_rec * passes / hot_s,
+            seconds_per_step=hot_s / passes,
+            value_1thread=n_rec / (r1["analyze_us"] * 1e-6),
+            pipeline_value=n_rec * passes / (r["run_wall_us"] * 1e-6),
+            motion_frames=int(r["par_motion_frames"]),
+            sample=f"first {n_frames} frames / {n_rec} records of the stream; reference sources (oracle/_ref): {threads} "
+            f"MotionScanner threads over disjoint ranges, {passes} timed passes, step time = slowest thread's own "
+            f"check_frame timer (hot path only); pipeline_value = ProcessingPipeline::run() wall incl. mmap + shim demux",
+        )
+    else:
+        gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
+        cfg = orc.make_cfg(params, gw, gh, m)
+        fpv = spec.frames_per_video or n_frames
+
+        def step(th):
+            flags, _ = orc.scan_frames(cfg, recs, off, early_exit=True, threads=th)  # reference semantics
+            for a in range(0, n_frames, fpv):
+                b = min(n_frames, a + fpv)
+                orc.video_tail(pts[a:b], flags[a:b], (b - a) / spec.fps, params.max_gap_sec, params.padding_sec, params.min_savings_pct)
+            return flags
+
+        for _ in range(warmup):
+            step(threads)
         t0 = time.perf_counter()
-        flags, _ = orc.scan_frames(cfg, recs, off, early_exit=False, threads=threads)
-        fpv = spec.frames_per_video or len(pts)
-        for a in range(0, len(pts), fpv):
-            b = min(len(pts), a + fpv)
-            orc.video_tail(pts[a:b], flags[a:b], (b - a) / spec.fps, params.max_gap_sec, params.padding_sec, params.min_savings_pct)
-        t_total += time.perf_counter() - t0
-        passes += 1
-        if t_total >= min_seconds or passes >= 50:
-            break
-    return n_rec * passes / t_total, passes, t_total
+        for _ in range(passes):
+            flags = step(threads)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        step(1)
+        dt1 = time.perf_counter() - t0
+        out.update(
+            kind="port",
+            value=n_rec * passes / dt,
+            seconds_per_step=dt / passes,
+            value_1thread=n_rec / dt1,
+            motion_frames=int(flags.sum()),
+            sample=f"first {n_frames} frames / {n_rec} records of the stream; oracle port (oracle/_ref not built), "
+            f"early-exit semantics + tail, {threads} pthreads, {passes} timed passes",
+        )
+    return out, n_rec
 
 
 def run_reference(args):
@@ -145,56 +211,30 @@ def run_reference(args):
     if rank != 0:
         return 0
     import motionscan as ms
-    import oracle_lib as orc
 
     threads = os.cpu_count() or 1
     params = ms.shipped_env_params()
     spec = ms.synth_preset(4, 5)
     n_frames = args.cpu_frames
-    cnt, off, recs, pts = host_sample(ms, spec, n_frames, threads)
-    n_rec = int(off[-1])
-    gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
-    cfg = orc.make_cfg(params, gw, gh, m)
-
-    def step():
-        flags, _ = orc.scan_frames(cfg, recs, off, early_exit=True, threads=threads)  # reference semantics
-        fpv = spec.frames_per_video or n_frames
-        for a in range(0, n_frames, fpv):
-            b = min(n_frames, a + fpv)
-            orc.video_tail(pts[a:b], flags[a:b], (b - a) / spec.fps, params.max_gap_sec, params.padding_sec, params.min_savings_pct)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = n_rec * args.steps / dt
-    kind = "port"
+    cpu, n_rec = cpu_leg(ms, params, spec, n_frames, threads, args.steps, args.warmup)
     line = {
         "impl": "reference",
         "metric": METRIC,
-        "value": value,
+        "value": cpu["value"],
         "unit": UNIT,
         "n_gpus": args.gpus,
         "steps": args.steps,
         "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3,
+        "ms_per_step": cpu["seconds_per_step"] * 1e3,
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "int32",
         "data": "synthetic",
         "config": workload_config(spec, n_frames, n_rec, "host"),
-        "frames_per_s": n_frames * args.steps / dt,
-        "cpu_baseline": {
-            "value": value,
-            "unit": UNIT,
-            "cores": threads,
-            "kind": kind,
-            "sample": f"{n_frames} frames / {n_rec} records of the same stream per step, early-exit (reference) semantics",
-        },
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": n_frames / cpu["seconds_per_step"],
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -374,26 +414,18 @@ def run_gpu(args):
         c_off = off[: c_frames + 1]
         c_recs = h_recs[: int(c_off[-1])]
         c_pts = h_pts[:c_frames]
-        v1, p1, t1 = cpu_scan_rate(ms, orc, params, spec, c_off, c_recs, c_pts, 1, args.cpu_seconds / 2)
-        vn, pn, tn = cpu_scan_rate(ms, orc, params, spec, c_off, c_recs, c_pts, threads, args.cpu_seconds / 2)
+        c_cnt = np.diff(c_off).astype(np.uint32)
+        cpu, _ = cpu_leg(ms, params, spec, c_frames, threads, 3, 1, sample_data=(c_cnt, c_off, c_recs, c_pts))
         # parity of the sample while we are here: oracle flags == GPU flags
         gw, gh, m = orc.geometry(spec.width, spec.height, params.block_size, params.block_shift, params.vertical_mask)
         of, _ = orc.scan_frames(orc.make_cfg(params, gw, gh, m), c_recs, c_off, threads=threads)
-        cpu = {
-            "value": vn,
-            "unit": UNIT,
-            "cores": threads,
-            "kind": "port",
-            "value_1thread": v1,
-            "sample": f"first {c_frames} frames / {int(c_off[-1])} records of the stream, full-count variant + tail, "
-            f"{pn} passes in {tn:.1f} s ({threads} threads), {p1} passes in {t1:.1f} s (1 thread)",
-            "parity_with_gpu": bool(np.array_equal(of, flags[:c_frames])),
-        }
+        cpu["parity_with_gpu"] = bool(np.array_equal(of, flags[:c_frames])) and cpu["motion_frames"] == int(of.sum())
 
     if rank == 0:
         peak, peak_src = peaks()
         ka_bytes = REC_BYTES * n_rec + FRAME_BYTES * n_frames
         achieved = ka_bytes / (ka_ms * 1e-3) / 1e9 if ka_ms > 0 else 0.0
+        traffic = measured_traffic(n_rec, n_frames)
         line = {
             "metric": METRIC,
             "value": value,
@@ -416,7 +448,8 @@ def run_gpu(args):
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic[0] if traffic else None,
+                "traffic_source": traffic[1] if traffic else None,
                 "peak_source": peak_src,
                 "bytes_per_launch": ka_bytes,
                 "ms_per_launch": ka_ms,
@@ -466,7 +499,6 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=9000, help="frames of the host-resident e2e sample (~4 GB)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-frames", type=int, default=3000, help="frames of the CPU-baseline sample")
-    ap.add_argument("--cpu-seconds", type=float, default=16.0)
     ap.add_argument("--slab-mb", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "motion_trim/config.hpp"
@@ -41,6 +42,12 @@ struct RefResult {
   int64_t decode_us;
   int64_t scan_wall_us;  // wall time of leg 1
   int64_t run_wall_us;   // wall time of leg 2, summed over the timed passes (warm-up passes excluded)
+  // leg 3: `threads` scanners over disjoint time ranges, like the pipeline's workers (pipeline.cpp:186-235),
+  // timed passes only
+  int64_t par_analyze_sum_us;  // Σ over threads and passes of the reference's analyze timer
+  int64_t par_analyze_max_us;  // Σ over passes of the slowest thread's analyze time (the hot path's wall time)
+  int64_t par_wall_us;         // Σ over passes of the leg's wall time (includes the shim's demux/"decode" copies)
+  int64_t par_motion_frames;   // timestamps found by the last pass (must equal n_ts)
 };
 
 int main(int argc, char** argv) {
@@ -95,6 +102,40 @@ int main(int argc, char** argv) {
     r.time_removed = pipe.get_time_removed();
     r.saved_pct = pipe.get_saved_pct();
     r.passes = (uint32_t)(p >= warmup ? p - warmup + 1 : 0);
+  }
+
+  if (r.scan_ok) {  // leg 3
+    MappedFile file;
+    if (!MemoryLoader::load_file(in, file)) return 3;
+    const int T = threads < 1 ? 1 : threads;
+    for (int p = 0; p < warmup + passes; ++p) {
+      std::vector<long> an(T, 0), found(T, 0);
+      std::vector<std::thread> th;
+      auto t0 = std::chrono::steady_clock::now();
+      for (int t = 0; t < T; ++t)
+        th.emplace_back([&, t] {
+          MotionScanner sc(file);
+          if (!sc.initialize()) return;
+          long seek_us = 0, decode_us = 0, analyze_us = 0;
+          const double a = r.duration * t / T, b = (t + 1 == T) ? r.duration : r.duration * (t + 1) / T;
+          found[t] = (long)sc.scan_range(a, b, seek_us, decode_us, analyze_us).size();
+          an[t] = analyze_us;
+        });
+      for (auto& x : th) x.join();
+      auto t1 = std::chrono::steady_clock::now();
+      if (p >= warmup) {
+        long mx = 0, tot = 0;
+        r.par_motion_frames = 0;
+        for (int t = 0; t < T; ++t) {
+          mx = std::max(mx, an[t]);
+          tot += an[t];
+          r.par_motion_frames += found[t];
+        }
+        r.par_analyze_sum_us += tot;
+        r.par_analyze_max_us += mx;
+        r.par_wall_us += std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+      }
+    }
   }
 
   r.n_ts = (uint32_t)ts.size();

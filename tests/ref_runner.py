@@ -12,7 +12,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 REF_BIN = ROOT / "oracle" / "_ref" / "ref_scan"
-RES = struct.Struct("<iiiIIIddddqqqq")  # RefResult in oracle/ref_harness.cpp
+RES = struct.Struct("<iiiIIIddddqqqqqqqq")  # RefResult in oracle/ref_harness.cpp
 
 
 def available() -> bool:
@@ -47,10 +47,11 @@ def run(mvs_path, params, threads=2, passes=1, warmup=0, chunk_sec=None, target_
                    stdout=subprocess.DEVNULL)
     raw = Path(out_path).read_bytes()
     (scan_ok, run_rc, decision, n_ts, n_segs, n_pass, duration, removed, pct, fps, analyze_us, decode_us, scan_wall_us,
-     run_wall_us) = RES.unpack_from(raw, 0)
+     run_wall_us, par_sum_us, par_max_us, par_wall_us, par_found) = RES.unpack_from(raw, 0)
     ts = np.frombuffer(raw, dtype="<f8", count=n_ts, offset=RES.size).copy()
     segs = np.frombuffer(raw, dtype="<f8", count=2 * n_segs, offset=RES.size + 8 * n_ts).reshape(-1, 2).copy()
     os.unlink(out_path)
     return dict(scan_ok=scan_ok, run_rc=run_rc, decision=decision, ts=ts, segs=segs, duration=duration,
                 time_removed=removed, saved_pct=pct, fps=fps, analyze_us=analyze_us, decode_us=decode_us,
-                scan_wall_us=scan_wall_us, run_wall_us=run_wall_us, passes=n_pass)
+                scan_wall_us=scan_wall_us, run_wall_us=run_wall_us, passes=n_pass, par_analyze_sum_us=par_sum_us,
+                par_analyze_max_us=par_max_us, par_wall_us=par_wall_us, par_motion_frames=par_found)
