@@ -214,8 +214,14 @@ def run_reference(args):
 
     threads = os.cpu_count() or 1
     params = ms.shipped_env_params()
-    spec = ms.synth_preset(4, 5)
+    global _WORKLOAD_DESC
+    preset, seed, _fixed, _WORKLOAD_DESC = WORKLOADS[args.workload]
+    spec = ms.synth_preset(preset, seed)
     n_frames = args.cpu_frames
+    if not n_frames:  # bounded sample: about --cpu-records records from the head of the stream
+        probe = np.zeros(64, np.uint32)
+        ms.lib().mscan_synth_host_counts(C.byref(spec), 0, 64, probe.ctypes.data, threads)
+        n_frames = max(1, int(np.ceil(args.cpu_records / max(probe.mean(), 1.0))))
     cpu, n_rec = cpu_leg(ms, params, spec, n_frames, threads, args.steps, args.warmup)
     line = {
         "impl": "reference",
@@ -241,10 +247,21 @@ def run_reference(args):
     return 0
 
 
+WORKLOADS = {
+    # name: (mvgen preset, seed, frames (None → sized by --records), description)
+    "stream1e9": (4, 5, None, "mvstream_1e9: decode-free synthetic AVMotionVector stream (BASELINE.json configs[4]), "
+                  "1080p30 CCTV mix cut into 10-min videos, native 40-B records"),
+    "cctv10min": (1, 2, 18000, "cctv10min: synthetic 10 min 1080p30 CCTV-style clip (BASELINE.json configs[1]) as an MV stream"),
+    "dense4k": (2, 3, 3600, "dense4k: synthetic 2 min 4K30 clip with a dense 8x8 MV field, 129 600 records per P-frame "
+                "(BASELINE.json configs[2]) as an MV stream"),
+    "batch64": (3, 100, 64 * 1800, "batch64: 64 synthetic 60 s 1080p30 clips in one batch (BASELINE.json configs[3]) as MV streams"),
+}
+_WORKLOAD_DESC = WORKLOADS["stream1e9"][3]
+
+
 def workload_config(spec, n_frames, n_rec, where):
     return {
-        "workload": "mvstream_1e9: decode-free synthetic AVMotionVector stream (BASELINE.json configs[4]), "
-        "1080p30 CCTV mix cut into 10-min videos, native 40-B records",
+        "workload": _WORKLOAD_DESC,
         "resident": where,
         "frames": int(n_frames),
         "records": int(n_rec),
@@ -294,15 +311,20 @@ def run_gpu(args):
     sh = stream.cuda_stream
 
     # ---- build the device-resident stream ---------------------------------------------------------
-    spec = ms.synth_preset(4, 5 + rank)
-    probe = 4096
-    d_probe = ctx.dev_alloc(4 * probe)
-    ctx.synth_counts(spec, 0, probe, d_probe, sh)
-    stream.synchronize()
-    pc = np.zeros(probe, np.uint32)
-    ctx.d2h(pc, d_probe)
-    ctx.dev_free(d_probe)
-    n_frames = int(np.ceil(args.records / max(pc.mean(), 1.0)))
+    global _WORKLOAD_DESC
+    preset, seed, fixed_frames, _WORKLOAD_DESC = WORKLOADS[args.workload]
+    spec = ms.synth_preset(preset, seed + rank)
+    if fixed_frames is None:
+        probe = 4096
+        d_probe = ctx.dev_alloc(4 * probe)
+        ctx.synth_counts(spec, 0, probe, d_probe, sh)
+        stream.synchronize()
+        pc = np.zeros(probe, np.uint32)
+        ctx.d2h(pc, d_probe)
+        ctx.dev_free(d_probe)
+        n_frames = int(np.ceil(args.records / max(pc.mean(), 1.0)))
+    else:
+        n_frames = fixed_frames
     d_cnt = ctx.dev_alloc(4 * n_frames)
     d_off = ctx.dev_alloc(8 * (n_frames + 1))
     ctx.synth_counts(spec, 0, n_frames, d_cnt, sh)
@@ -364,7 +386,10 @@ def run_gpu(args):
     ctx.d2h(res, d_res)
 
     # ---- e2e: host-fed through the C ABI ------------------------------------------------------------
-    e2e_frames = min(args.e2e_frames, n_frames)
+    # host-resident sample: the leading frames of the stream, bounded by --e2e-records (~3.6 GB pinned)
+    e2e_frames = int(min(max(np.searchsorted(off, np.uint64(int(args.e2e_records)), side="right") - 1, 1), n_frames))
+    if args.e2e_frames:
+        e2e_frames = min(args.e2e_frames, n_frames)
     e_rec = int(off[e2e_frames])
     h_recs = ctx.pinned_array(e_rec, ms.MV_DTYPE)
     h_pts = ctx.pinned_array(e2e_frames, np.float64)
@@ -410,7 +435,9 @@ def run_gpu(args):
         import oracle_lib as orc
 
         threads = os.cpu_count() or 1
-        c_frames = min(args.cpu_frames, e2e_frames)
+        c_frames = int(min(max(np.searchsorted(off, np.uint64(int(args.cpu_records)), side="right") - 1, 1), e2e_frames))
+        if args.cpu_frames:
+            c_frames = min(args.cpu_frames, e2e_frames)
         c_off = off[: c_frames + 1]
         c_recs = h_recs[: int(c_off[-1])]
         c_pts = h_pts[:c_frames]
@@ -495,10 +522,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--records", type=float, default=1e9, help="records per GPU in the device-resident stream")
-    ap.add_argument("--e2e-frames", type=int, default=9000, help="frames of the host-resident e2e sample (~4 GB)")
+    ap.add_argument("--workload", default="stream1e9", choices=sorted(WORKLOADS))
+    ap.add_argument("--records", type=float, default=1e9, help="records per GPU in the device-resident stream (stream1e9)")
+    ap.add_argument("--e2e-records", type=float, default=9e7, help="records of the host-resident e2e sample (~3.6 GB pinned)")
+    ap.add_argument("--e2e-frames", type=int, default=0, help="override: frames of the e2e sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-frames", type=int, default=3000, help="frames of the CPU-baseline sample")
+    ap.add_argument("--cpu-records", type=float, default=3e7, help="records of the CPU-baseline / reference-arm sample")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="override: frames of the CPU sample")
     ap.add_argument("--slab-mb", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
