@@ -274,36 +274,18 @@ def workload_config(spec, n_frames, n_rec, where):
 # ---------------------------------------------------------------------------------- GPU arm -------
 def run_gpu(args):
     import torch
-    import torch.distributed as dist
 
     import motionscan as ms
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
+    from motionscan.dist import Dist, throughput
+
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the motion-scan path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def allmax(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    D = Dist("nccl", torch.device("cuda", local))
+    world, rank = D.world, D.rank
+    barrier, allmax, allsum = D.barrier, D.allmax, D.allsum
 
     params = ms.shipped_env_params()
     ctx = ms.Context(local, params, max_log_frames=1 << 20, slab_bytes=args.slab_mb << 20)
@@ -377,7 +359,7 @@ def run_gpu(args):
     launches = int(st.scan_launches + st.segment_launches)
     total_rec = allsum(float(n_rec))
     total_frames = allsum(float(n_frames))
-    value = total_rec * args.steps / (ms_total * 1e-3)
+    value = throughput(total_rec, args.steps, ms_total)
 
     # sanity on the results of the last step (not timed): flags must be a mix, every video decided
     flags = np.zeros(n_frames, np.uint8)
@@ -511,8 +493,7 @@ def run_gpu(args):
     ctx.host_free(h_recs.ctypes.data)
     ctx.host_free(h_pts.ctypes.data)
     ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

@@ -155,13 +155,18 @@ int mscan_video_open_geometry(mscan_ctx* ctx, uint32_t video_id, const mscan_geo
  * native layout; rec_count[i] == 0 means "no MV side data" (motion_scanner.cpp:219-221).
  * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / cudaHostRegister) it is DMA'd
  * in place and must stay valid until mscan_flush/mscan_collect returns; pageable memory is
- * copied into the library's pinned ring before the call returns. */
+ * copied into the library's pinned ring before the call returns.
+ * first_frame_out (may be NULL): index, in the video's submission order, of this call's first
+ * frame — what a chunk worker needs to read back its own frames with mscan_collect_range. */
 int mscan_submit(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
-                 const uint32_t* rec_count, const mscan_mv* recs);
+                 const uint32_t* rec_count, const mscan_mv* recs, uint64_t* first_frame_out);
 int mscan_flush(mscan_ctx* ctx); /* launch whatever is staged; does not wait */
 /* Per-frame results in submission order. cap = capacity of flags/full_counts (either may be NULL). */
 int mscan_collect(mscan_ctx* ctx, uint32_t video_id, uint8_t* flags, uint32_t* full_counts,
                   uint32_t cap, uint32_t* n_frames_out);
+/* Frames [first, first+n) of the video's submission order (one chunk's scan_range result). */
+int mscan_collect_range(mscan_ctx* ctx, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags,
+                        uint32_t* full_counts);
 /* Segments for the FFmpegJob of one video: on MSCAN_CUT the clamped motion segments, on
  * MSCAN_FULL_COPY the single {0,duration}, on MSCAN_NO_MOTION none. MSCAN_ERR_CAPACITY if
  * cap is too small (n_out still reports the needed count). */

@@ -1,5 +1,5 @@
 /*
- * mvs_format.h — the MVS1 motion-vector stream file: what FFmpeg's export_mvs decode of one video
+ * mvs_format.h — the MVS1 motion-vector stream file (shared by the product CLI and the test shim): what FFmpeg's export_mvs decode of one video
  * would hand to the scanner, frozen to disk. Used as the input container of the fake-libav shim
  * (oracle/_ref) and as the decode-free input of the product CLI.
  *

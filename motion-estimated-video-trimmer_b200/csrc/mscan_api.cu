@@ -658,15 +658,23 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
 }
 
 int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                 const mscan_mv* recs) {
+                 const mscan_mv* recs, uint64_t* first_frame_out) {
   if (!c) return MSCAN_ERR_INVALID;
-  if (n_frames == 0) return MSCAN_OK;
+  if (n_frames == 0) {
+    if (first_frame_out) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      auto it0 = c->videos.find(video_id);
+      *first_frame_out = it0 == c->videos.end() ? 0 : it0->second.n_frames;
+    }
+    return MSCAN_OK;
+  }
   if (!pts || !rec_count) return fail(c, MSCAN_ERR_INVALID, "null pts/rec_count");
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
   Video& v = it->second;
+  if (first_frame_out) *first_frame_out = v.n_frames;
   if (c->log_head + n_frames > c->log_cap) {
     if (c->videos.size() == 1 && v.n_frames == 0 && n_frames <= c->log_cap) {
       int rc = sync_scans_locked(c);
@@ -765,6 +773,33 @@ int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* cou
     if (counts) CU(cudaMemcpyAsync(counts + at, c->d_counts + e.start, e.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
     c->stats.d2h_bytes += (flags ? e.n : 0) + (counts ? 4 * e.n : 0);
     at += e.n;
+  }
+  CU(cudaStreamSynchronize(c->main_stream));
+  return MSCAN_OK;
+}
+
+int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags, uint32_t* counts) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  const Video& v = it->second;
+  if (first + n > v.n_frames) return fail(c, MSCAN_ERR_INVALID, "range [%llu,+%u) exceeds the video's %llu frames",
+                                          (unsigned long long)first, n, (unsigned long long)v.n_frames);
+  int rc = sync_scans_locked(c);
+  if (rc) return rc;
+  uint64_t pos = 0, out = 0;  // pos: video-local index of the current extent's first frame
+  for (const Extent& e : v.extents) {
+    const uint64_t a = std::max<uint64_t>(first, pos), b = std::min<uint64_t>(first + n, pos + e.n);
+    if (a < b) {
+      const uint64_t src = e.start + (a - pos), m = b - a;
+      if (flags) CU(cudaMemcpyAsync(flags + out, c->d_flags + src, m, cudaMemcpyDeviceToHost, c->main_stream));
+      if (counts) CU(cudaMemcpyAsync(counts + out, c->d_counts + src, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
+      c->stats.d2h_bytes += (flags ? m : 0) + (counts ? 4 * m : 0);
+      out += m;
+    }
+    pos += e.n;
   }
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;

@@ -1,0 +1,49 @@
+// batch_processor.hpp — host mirror of BatchProcessor (reference include/motion_trim/batch_processor.hpp:77-147):
+// BatchProcessor(parallel_streams), process(files, output_dir, input_dir) → number of failures.
+// The reference deals files from one queue to PARALLEL_STREAMS CPU stream threads
+// (src/batch_processor.cpp:152-157,215-235,307-382); here the same queue feeds PARALLEL_STREAMS stream
+// threads PER GPU, each bound to its GPU's context — videos are independent, so GPUs never exchange data.
+#pragma once
+
+#include <atomic>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "ffmpeg_queue.hpp"
+#include "gpu_pool.hpp"
+
+namespace motion_trim {
+
+struct StreamResult {
+  std::string file;
+  int gpu = 0;
+  int rc = 0;
+  int decision = 0;
+  double seconds = 0, duration = 0, time_removed = 0, saved_pct = 0;
+  uint64_t frames = 0, records = 0;
+  size_t n_segments = 0;
+};
+
+class BatchProcessor {
+ public:
+  explicit BatchProcessor(int parallel_streams);
+  int process(const std::vector<std::string>& input_files, const std::string& output_dir,
+              const std::string& input_dir = "");
+  const std::vector<StreamResult>& results() const { return results_; }
+
+ private:
+  bool next_file(std::string& out);
+  void stream_worker(int stream_id, int gpu, const std::string& output_dir);
+
+  int streams_per_gpu_;
+  GpuPool pool_;
+  FFmpegQueue ffmpeg_queue_;
+  std::mutex queue_mu_, results_mu_;
+  std::queue<std::string> work_;
+  std::vector<StreamResult> results_;
+  std::atomic<int> failures_{0};
+};
+
+}  // namespace motion_trim

@@ -1,0 +1,95 @@
+// ffmpeg_queue.cpp — job queue + muxing step (contract of reference src/ffmpeg_queue.cpp and
+// src/ffmpeg_executor.cpp:24-118; see ffmpeg_queue.hpp).
+#include "motion_trim/ffmpeg_queue.hpp"
+
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <fstream>
+
+namespace motion_trim {
+
+void FFmpegQueue::push(FFmpegJob job) {
+  {
+    std::lock_guard<std::mutex> lk(mutex_);
+    jobs_.push(std::move(job));
+  }
+  cv_.notify_one();
+}
+
+bool FFmpegQueue::pop(FFmpegJob& job) {
+  std::unique_lock<std::mutex> lk(mutex_);
+  cv_.wait(lk, [this] { return !jobs_.empty() || done_.load(); });
+  if (jobs_.empty()) return false;
+  job = std::move(jobs_.front());
+  jobs_.pop();
+  return true;
+}
+
+void FFmpegQueue::finish() {
+  done_.store(true);
+  cv_.notify_all();
+}
+
+bool FFmpegQueue::empty() const {
+  std::lock_guard<std::mutex> lk(mutex_);
+  return jobs_.empty();
+}
+
+std::string build_concat_list(const std::string& input_path, const std::vector<TimeSegment>& segments) {
+  const std::string abs = std::filesystem::absolute(input_path).string();
+  std::string out;
+  char line[64];
+  for (const TimeSegment& s : segments) {
+    if (s.end <= s.start) continue;
+    out += "file '" + abs + "'\n";
+    std::snprintf(line, sizeof line, "inpoint %.2f\n", s.start);
+    out += line;
+    std::snprintf(line, sizeof line, "outpoint %.2f\n", s.end);
+    out += line;
+  }
+  return out;
+}
+
+static std::string find_ffmpeg() {
+  if (const char* e = std::getenv("MOTION_TRIM_FFMPEG")) return e;
+  const char* dflt = "/usr/local/bin/ffmpeg";
+  return access(dflt, X_OK) == 0 ? dflt : "";
+}
+
+int execute_ffmpeg_cut(const std::string& input_path, const std::string& output_path,
+                       const std::vector<TimeSegment>& segments, const std::vector<int>& cpu_set, int stream_id) {
+  if (segments.empty()) {
+    std::printf("[WARN] %sNo segments to cut\n", stream_id >= 0 ? ("[Stream " + std::to_string(stream_id) + "] ").c_str() : "");
+    return 0;
+  }
+  const std::string list = build_concat_list(input_path, segments);
+  const std::string ffmpeg = find_ffmpeg();
+  const std::string list_path = output_path + ".concat.txt";
+  {
+    std::ofstream f(list_path, std::ios::binary);
+    if (!f) return -1;
+    f << list;
+  }
+  if (ffmpeg.empty()) {
+    std::printf("[WARN] no ffmpeg binary in this image: wrote %s instead of cutting\n", list_path.c_str());
+    return 0;
+  }
+  std::string cmd;
+  if (!cpu_set.empty()) {
+    cmd = "taskset -c ";
+    for (size_t i = 0; i < cpu_set.size(); ++i) cmd += (i ? "," : "") + std::to_string(cpu_set[i]);
+    cmd += " ";
+  }
+  cmd += ffmpeg + " -y -hide_banner -loglevel error -f concat -safe 0 -i \"" + list_path +
+         "\" -c copy -fflags +genpts -avoid_negative_ts make_zero -movflags +faststart \"" + output_path + "\"";
+  const int status = std::system(cmd.c_str());
+  std::remove(list_path.c_str());
+  if (status != 0) std::printf("[ERROR] FFmpeg failed with status %d\n", status);
+  return status;
+}
+
+}  // namespace motion_trim

@@ -1,0 +1,35 @@
+// gpu_pool.cpp — libmotionscan contexts, one per GPU.
+#include "motion_trim/gpu_pool.hpp"
+
+namespace motion_trim {
+
+GpuPool::~GpuPool() {
+  for (mscan_ctx* c : ctx_) mscan_destroy(c);
+}
+
+bool GpuPool::open(int max_gpus) {
+  int rc = mscan_params_from_env(&params_);
+  if (rc != MSCAN_OK) {
+    error_ = "unparsable motion_trim environment knob";
+    return false;
+  }
+  int n = 0;
+  rc = mscan_device_count(&n);
+  if (rc != MSCAN_OK || n <= 0) {
+    error_ = "no CUDA device (libmotionscan has no CPU fallback)";
+    return false;
+  }
+  if (max_gpus > 0 && max_gpus < n) n = max_gpus;
+  for (int g = 0; g < n; ++g) {
+    mscan_ctx* c = nullptr;
+    rc = mscan_create(g, &params_, 0, 0, &c);
+    if (rc != MSCAN_OK) {
+      error_ = std::string("mscan_create failed: ") + mscan_status_string(rc);
+      return false;
+    }
+    ctx_.push_back(c);
+  }
+  return true;
+}
+
+}  // namespace motion_trim

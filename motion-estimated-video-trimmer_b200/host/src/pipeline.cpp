@@ -1,0 +1,160 @@
+// pipeline.cpp — host mirror of ProcessingPipeline::run (reference src/pipeline.cpp:89-415).
+// Phases kept: map file (:95), probe (:108-125), chunk queue (:141-167), worker threads each with a
+// private scanner (:186-235), decision + FFmpegJob (:358-404). Phases moved to the GPU: check_frame
+// inside the workers, and merge/segment/savings (:297-356) as one mscan_segments call.
+#include "motion_trim/pipeline.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <filesystem>
+#include <mutex>
+#include <thread>
+
+#include "motion_trim/config.hpp"
+#include "motion_trim/gpu_pool.hpp"
+#include "motion_trim/motion_scanner.hpp"
+
+namespace motion_trim {
+
+namespace {
+std::mutex g_log_mu;
+void logf(int stream_id, const char* level, const std::string& msg) {
+  std::lock_guard<std::mutex> lk(g_log_mu);
+  if (stream_id >= 0) std::printf("%s[Stream %d] %s\n", level, stream_id, msg.c_str());
+  else std::printf("%s%s\n", level, msg.c_str());
+  std::fflush(stdout);
+}
+}  // namespace
+
+ProcessingPipeline::ProcessingPipeline(std::string in, std::string out, int stream_id, int num_threads,
+                                       std::vector<int> cpu_set)
+    : input_path_(std::move(in)), output_path_(std::move(out)), stream_id_(stream_id), num_threads_(num_threads),
+      cpu_set_(std::move(cpu_set)) {}
+
+void ProcessingPipeline::set_gpu(GpuPool* pool, int gpu_index) {
+  pool_ = pool;
+  gpu_index_ = gpu_index;
+}
+
+int ProcessingPipeline::run() {
+  if (!pool_ || gpu_index_ < 0 || gpu_index_ >= pool_->size()) {
+    logf(stream_id_, "[ERROR] ", "no GPU context (the motion scan has no CPU fallback)");
+    return 1;
+  }
+  mscan_ctx* gpu = pool_->ctx(gpu_index_);
+  if (!MemoryLoader::load_file(input_path_, file_buffer_)) {
+    logf(stream_id_, "[ERROR] ", "Failed to map file: " + input_path_);
+    return 1;
+  }
+  const uint32_t video_id = pool_->next_video_id();
+  double fps = 0;
+  int width = 0, height = 0;
+  {
+    MotionScanner probe(file_buffer_, gpu, video_id);
+    if (!probe.initialize()) {
+      logf(stream_id_, "[ERROR] ", "Failed to initialize probe (not an MVS1 motion-vector stream?)");
+      return 1;
+    }
+    duration_ = probe.get_duration();
+    fps = probe.get_fps();
+    width = probe.width();
+    height = probe.height();
+  }
+  if (!(duration_ > 0)) {  // the reference divides by zero here (pipeline.cpp:141-143,259); refuse instead
+    logf(stream_id_, "[ERROR] ", "stream has no duration");
+    return 1;
+  }
+  if (mscan_video_open(gpu, video_id, width, height) != MSCAN_OK) {
+    logf(stream_id_, "[ERROR] ", std::string("mscan_video_open: ") + mscan_last_error(gpu));
+    return 1;
+  }
+  char buf[160];
+  std::snprintf(buf, sizeof buf, "Duration: %.2fs (%.0f frames @ %.1ffps) on GPU %d", duration_, duration_ * fps, fps, gpu_index_);
+  logf(stream_id_, "[INFO] ", buf);
+
+  // ---- chunk queue + workers (the workers are the decode front-end; here they walk the MVS index)
+  const double chunk = Config::chunk_duration_sec();
+  std::vector<ScanTask> tasks;
+  int id = 0;
+  for (double t = 0; t < duration_; t += chunk) tasks.push_back(ScanTask{t, std::min(t + chunk, duration_), id++});
+  int n_threads = num_threads_ > 0 ? num_threads_ : std::max(2u, std::thread::hardware_concurrency());
+  n_threads = std::max(1, std::min<int>(n_threads, (int)tasks.size()));
+  std::atomic<size_t> next{0};
+  std::atomic<long> frames{0};
+  std::atomic<bool> failed{false};
+  std::vector<std::thread> workers;
+  for (int w = 0; w < n_threads; ++w)
+    workers.emplace_back([&] {
+      MotionScanner scanner(file_buffer_, gpu, video_id);
+      if (!scanner.initialize()) {
+        failed = true;
+        return;
+      }
+      long seek_us = 0, decode_us = 0;
+      for (size_t k = next.fetch_add(1); k < tasks.size(); k = next.fetch_add(1)) {
+        const long n = scanner.scan_range_async(tasks[k].start, tasks[k].end, seek_us, decode_us);
+        if (n < 0) {
+          failed = true;
+          return;
+        }
+        frames += n;
+      }
+    });
+  for (auto& t : workers) t.join();
+  frames_scanned_ = (uint64_t)frames.load();
+  if (failed) {
+    logf(stream_id_, "[ERROR] ", std::string("scan failed: ") + mscan_last_error(gpu));
+    mscan_video_close(gpu, video_id);
+    return 1;
+  }
+
+  // ---- merge + segments + savings + decision on the GPU (pipeline.cpp:297-358)
+  segments_.assign(64, TimeSegment{0, 0});
+  uint32_t n_seg = 0;
+  mscan_video_result res{};
+  int rc = mscan_segments(gpu, video_id, duration_, reinterpret_cast<mscan_segment*>(segments_.data()),
+                          (uint32_t)segments_.size(), &n_seg, &res);
+  if (rc == MSCAN_ERR_CAPACITY) {
+    segments_.assign(n_seg, TimeSegment{0, 0});
+    rc = mscan_segments(gpu, video_id, duration_, reinterpret_cast<mscan_segment*>(segments_.data()),
+                        (uint32_t)segments_.size(), &n_seg, &res);
+  }
+  mscan_video_close(gpu, video_id);
+  if (rc != MSCAN_OK) {
+    logf(stream_id_, "[ERROR] ", std::string("mscan_segments: ") + mscan_last_error(gpu));
+    return 1;
+  }
+  segments_.resize(n_seg);
+  decision_ = res.decision;
+  time_removed_ = res.time_removed;
+  saved_pct_ = res.saved_pct;
+  std::snprintf(buf, sizeof buf, "Scanned %llu frames, found %u motion frames", (unsigned long long)frames_scanned_, res.n_motion_frames);
+  logf(stream_id_, "[INFO] ", buf);
+
+  if (decision_ == MSCAN_NO_MOTION) {  // :308-319 — warn, return 0, no job, no output file
+    logf(stream_id_, "[WARN] ", "No motion found.");
+    return 0;
+  }
+  if (decision_ == MSCAN_FULL_COPY) {
+    std::snprintf(buf, sizeof buf, "Savings too low (%d%%). Min required: %d%%. Copying full stream.", (int)saved_pct_,
+                  (int)Config::min_savings_pct());
+    logf(stream_id_, "[WARN] ", buf);
+  }
+  if (ffmpeg_queue_) {
+    FFmpegJob job;
+    job.stream_id = stream_id_;
+    job.input_path = std::filesystem::absolute(input_path_).string();
+    job.output_path = output_path_;
+    job.segments = segments_;
+    job.cpu_set = cpu_set_;
+    ffmpeg_queue_->push(std::move(job));
+    logf(stream_id_, "[INFO] ", decision_ == MSCAN_CUT ? "Pushed FFmpeg job to queue" : "Pushed full-copy job to queue");
+    return 0;
+  }
+  return execute_ffmpeg_cut(input_path_, output_path_, segments_, cpu_set_, stream_id_) == 0 ? 0 : 1;
+}
+
+}  // namespace motion_trim

@@ -129,7 +129,8 @@ SYMBOLS = {
     "mscan_set_profiling": (_i, [_vp, _i]),
     "mscan_video_open": (_i, [_vp, _u32, _i, _i]),
     "mscan_video_open_geometry": (_i, [_vp, _u32, _P(Geometry)]),
-    "mscan_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _vp]),
+    "mscan_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _P(_u64)]),
+    "mscan_collect_range": (_i, [_vp, _u32, _u64, _u32, _vp, _vp]),
     "mscan_flush": (_i, [_vp]),
     "mscan_collect": (_i, [_vp, _u32, _vp, _vp, _u32, _P(_u32)]),
     "mscan_segments": (_i, [_vp, _u32, _d, _vp, _u32, _P(_u32), _P(VideoResult)]),
@@ -274,12 +275,21 @@ class Context:
     def video_open_geometry(self, vid: int, g: Geometry):
         self._ck(self.L.mscan_video_open_geometry(self.h, vid, C.byref(g)))
 
-    def submit(self, vid: int, pts, rec_count, recs):
+    def submit(self, vid: int, pts, rec_count, recs) -> int:
+        """Returns the video-local index of the first submitted frame."""
         n = len(rec_count)
-        self._ck(self.L.mscan_submit(self.h, vid, n, _ptr(pts), _ptr(rec_count), _ptr(recs)))
+        first = C.c_uint64()
+        self._ck(self.L.mscan_submit(self.h, vid, n, _ptr(pts), _ptr(rec_count), _ptr(recs), C.byref(first)))
+        return first.value
 
     def submit_raw(self, vid: int, n_frames: int, pts_ptr: int, cnt_ptr: int, recs_ptr: int):
-        self._ck(self.L.mscan_submit(self.h, vid, n_frames, pts_ptr, cnt_ptr, recs_ptr))
+        self._ck(self.L.mscan_submit(self.h, vid, n_frames, pts_ptr, cnt_ptr, recs_ptr, None))
+
+    def collect_range(self, vid: int, first: int, n: int):
+        flags = np.zeros(n, dtype=np.uint8)
+        counts = np.zeros(n, dtype=np.uint32)
+        self._ck(self.L.mscan_collect_range(self.h, vid, first, n, _ptr(flags), _ptr(counts)))
+        return flags, counts
 
     def flush(self):
         self._ck(self.L.mscan_flush(self.h))

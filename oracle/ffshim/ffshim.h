@@ -3,7 +3,7 @@
  * own sources (src/motion_scanner.cpp, src/memory_io.cpp, src/pipeline.cpp) unmodified from
  * /root/reference. TEST INFRASTRUCTURE ONLY (oracle/_ref); nothing here is FFmpeg code.
  *
- * The "container" it demuxes is the MVS1 stream file (oracle/ffshim/mvs_format.h): per frame a pts,
+ * The "container" it demuxes is the MVS1 stream file (include/mvs_format.h): per frame a pts,
  * a keyframe bit and the AVMotionVector records export_mvs would have attached. "Decoding" a packet
  * hands those records back as AV_FRAME_DATA_MOTION_VECTORS side data, so MotionScanner::scan_range →
  * check_frame and ProcessingPipeline::run execute exactly the reference's code on our MV streams.

@@ -1,4 +1,4 @@
-"""MVS1 motion-vector stream files (oracle/ffshim/mvs_format.h): writer/reader used by the tests, the
+"""MVS1 motion-vector stream files (include/mvs_format.h): writer/reader used by the tests, the
 reference runner and the golden-fixture generator."""
 from __future__ import annotations
 
