@@ -7,6 +7,8 @@
  *   vote()                src/motion_scanner.cpp:229-268   (Phase 0 + Phase 1)
  *   orc_check_frame       src/motion_scanner.cpp:217-295   (Phase 2 with early exit :288-289)
  *   orc_full_count        same Phase 2 with the early exit removed
+ *   orc_select_range      src/motion_scanner.cpp:303-371   (frame skip, seek, pts, range filter)
+ *   orc_select_pipeline   src/pipeline.cpp:163-167         (chunk queue) + orc_select_range per chunk
  *   orc_merge_timestamps  src/pipeline.cpp:302-304
  *   orc_build_segments    src/pipeline.cpp:325-344
  *   orc_savings           src/pipeline.cpp:349-356
@@ -175,6 +177,42 @@ void orc_scan_frames_mt(const orc_cfg* c, const void* recs, const uint64_t* rec_
   for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
   free(jobs);
   free(th);
+}
+
+uint32_t orc_select_range(const int64_t* pts_ticks, const uint8_t* is_key, uint32_t n_frames, double time_base,
+                          double video_fps, double target_fps, double start, double end, uint32_t* out_idx) {
+  const int frame_skip = (target_fps > 0 && target_fps < video_fps) ? (int)(video_fps / target_fps) : 1; /* :310-313 */
+  int frame_count = 0;                                                                                   /* :314 */
+  uint32_t i = 0;
+  if (start > 0) {                                                                                       /* :321-325 */
+    const int64_t seek_ts = (int64_t)(start / time_base);
+    uint32_t best = 0;
+    for (uint32_t k = 0; k < n_frames; ++k) {
+      if (!is_key[k]) continue;
+      if (pts_ticks[k] <= seek_ts) best = k;
+      else break;
+    }
+    i = best;
+  }
+  uint32_t n = 0;
+  for (; i < n_frames; ++i) {
+    if (++frame_count % frame_skip != 0) continue;                                                       /* :357 */
+    const double pts = (double)pts_ticks[i] * time_base;                                                 /* :361 */
+    if (pts < start) continue;                                                                           /* :364 */
+    if (pts >= end) break;                                                                               /* :368 */
+    out_idx[n++] = i;                                                                                    /* :376 */
+  }
+  return n;
+}
+
+uint32_t orc_select_pipeline(const int64_t* pts_ticks, const uint8_t* is_key, uint32_t n_frames, double time_base,
+                             double video_fps, double target_fps, double duration, double chunk_sec, uint32_t* out_idx) {
+  uint32_t n = 0;
+  for (double t = 0; t < duration; t += chunk_sec) {                                                     /* :163 */
+    const double end = (t + chunk_sec < duration) ? t + chunk_sec : duration;                            /* :164 std::min */
+    n += orc_select_range(pts_ticks, is_key, n_frames, time_base, video_fps, target_fps, t, end, out_idx + n);
+  }
+  return n;
 }
 
 static int cmp_double(const void* a, const void* b) {

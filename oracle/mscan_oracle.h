@@ -61,6 +61,16 @@ void orc_scan_frames(const orc_cfg* c, const void* recs, const uint64_t* rec_off
 void orc_scan_frames_mt(const orc_cfg* c, const void* recs, const uint64_t* rec_off, uint32_t n_frames,
                         uint8_t* flags, uint32_t* counts, int early_exit, int n_threads);
 
+/* src/motion_scanner.cpp:303-371: the frames ONE scan_range(start,end) call hands to check_frame.
+ * pts_ticks/is_key describe the stream in decode order; the seek lands on the last key frame whose
+ * pts <= (int64)(start/time_base) (AVSEEK_FLAG_BACKWARD; frame 0 when there is none), the skip counter
+ * starts there (:314,:357 precede the range test :364). Writes frame indices, returns how many. */
+uint32_t orc_select_range(const int64_t* pts_ticks, const uint8_t* is_key, uint32_t n_frames, double time_base,
+                          double video_fps, double target_fps, double start, double end, uint32_t* out_idx);
+/* src/pipeline.cpp:163-167 chunking + one orc_select_range per chunk; indices in chunk order. */
+uint32_t orc_select_pipeline(const int64_t* pts_ticks, const uint8_t* is_key, uint32_t n_frames, double time_base,
+                             double video_fps, double target_fps, double duration, double chunk_sec, uint32_t* out_idx);
+
 /* src/pipeline.cpp:302-304: sort + unique in place; returns the new length. */
 uint32_t orc_merge_timestamps(double* ts, uint32_t n);
 /* src/pipeline.cpp:325-344: returns the number of segments written (ts sorted-unique, n >= 1). */

@@ -7,7 +7,9 @@ compiled unmodified against the fake-libav shim) over the cases in tests/golden_
 
 Needs /root/reference (only present in the build container). The fixture stores, per case, the
 input digest and the reference's outputs: timestamps with motion (scan_range), the FFmpegJob
-segments, decision, duration, time_removed and saved_pct — doubles as hex strings, exact.
+segments, decision, duration, time_removed and saved_pct — doubles as hex strings, exact. `ts` comes from ONE
+scan_range(0, duration) call; the job comes from the chunked, multi-threaded pipeline (the two differ
+when TARGET_FPS skips frames, because the skip counter restarts at every chunk's seek key frame).
 """
 import json
 import sys
@@ -31,7 +33,7 @@ def main():
             path = Path(d) / (c.name + ".mvs")
             mvs_io.write_mvs(path, c.width, c.height, c.fps[0], c.fps[1], c.ticks, c.cnt, c.recs, has_mvs=c.has_mvs,
                              tb_num=c.tb[0], tb_den=c.tb[1], duration_us=c.duration_us)
-            r = ref_runner.run(path, c.params, threads=c.threads, chunk_sec=c.chunk_sec)
+            r = ref_runner.run(path, c.params, threads=c.threads, chunk_sec=c.chunk_sec, target_fps=c.target_fps)
             assert r["scan_ok"] == 1 and r["run_rc"] == 0, c.name
             assert r["duration"] == c.duration, (c.name, r["duration"], c.duration)
             out["cases"][c.name] = {
@@ -41,6 +43,7 @@ def main():
                 "params": gc.params_dict(c.params),
                 "chunk_sec": c.chunk_sec,
                 "threads": c.threads,
+                "target_fps": c.target_fps,
                 "duration": float(r["duration"]).hex(),
                 "ts": [float(t).hex() for t in r["ts"]],
                 "segments": [[float(a).hex(), float(b).hex()] for a, b in r["segs"]],

@@ -39,15 +39,40 @@ class Case:
     """One video: frames (rec_count, recs), pts ticks + time base, fps, params, reference run options."""
 
     def __init__(self, name, width, height, fps, tb, ticks, cnt, recs, params, has_mvs=None, chunk_sec=None, threads=2,
-                 duration_us=None):
+                 duration_us=None, target_fps=None):
         self.name, self.width, self.height, self.fps, self.tb = name, width, height, fps, tb
         self.ticks = np.asarray(ticks, dtype=np.int64)
         self.cnt = np.asarray(cnt, dtype=np.uint32)
         self.recs = recs
         self.params = params
-        self.has_mvs = has_mvs
+        self.has_mvs = np.asarray(has_mvs, dtype=bool) if has_mvs is not None else (self.cnt > 0)
+        # same default as mvs_io.write_mvs: frame 0 and every frame without vectors (I-frames) are seek points
+        self.key = ~self.has_mvs
+        self.key[0:1] = True
         self.chunk_sec, self.threads = chunk_sec, threads
         self.duration_us = duration_us
+        self.target_fps = target_fps
+
+    # ---- what the reference's host code does before check_frame (motion_scanner.cpp:303-371) ----
+    def selected(self, chunked=True):
+        """Frame indices handed to check_frame: by the chunked pipeline (default) or by one
+        scan_range(0, duration) call."""
+        import oracle_lib as orc
+
+        fps = self.fps[0] / float(self.fps[1])
+        chunk = (self.chunk_sec or 30.0) if chunked else self.duration + 1.0
+        return orc.select_pipeline(self.ticks, self.key, self.tb[0] / float(self.tb[1]), fps, self.target_fps or 0.0,
+                                   self.duration, chunk)
+
+    def subset(self, idx):
+        """(rec_count, rec_off, recs, pts) restricted to frames idx, in that order."""
+        off = self.off
+        cnt = np.where(self.has_mvs[idx], self.cnt[idx], 0).astype(np.uint32)
+        parts = [self.recs[int(off[i]) : int(off[i + 1])] for i, h in zip(idx, self.has_mvs[idx]) if h]
+        recs = kats.cat(*parts)
+        o = np.zeros(len(idx) + 1, dtype=np.uint64)
+        np.cumsum(cnt, out=o[1:])
+        return cnt, o, recs, self.pts[idx]
 
     @property
     def off(self):
@@ -146,4 +171,9 @@ def all_cases():
     cases.append(synth_case("dense_4k_24f", 2, 3, 24, E()))                                  # configs[2] shape
     cases.append(synth_case("stream_cfg4_720f", 4, 5, 720, E(), chunk_sec=6.0, threads=4))   # configs[4] slice
     cases += random_param_cases()
+    # TARGET_FPS frame skipping: the counter restarts at each chunk's seek key frame
+    cases.append(synth_case("skip_tfps10_chunk10", 3, 102, 900, E(), chunk_sec=10.0, threads=3, target_fps=10.0))
+    cases.append(synth_case("skip_tfps7_chunk2p5", 0, 103, 600, E(), chunk_sec=2.5, threads=4, target_fps=7.0))
+    cases.append(synth_case("skip_tfps4_chunk7", 3, 104, 900, kats.code_defaults(), chunk_sec=7.0, threads=2, target_fps=4.0))
+    cases.append(synth_case("skip_tfps12p5_720p", 0, 105, 450, E(), 1280, 720, chunk_sec=30.0, threads=1, target_fps=12.5))
     return cases

@@ -53,6 +53,10 @@ def lib():
         L.orc_scan_frames.restype = None
         L.orc_scan_frames_mt.argtypes = [C.POINTER(OrcCfg), vp, vp, u32, vp, vp, i, i]
         L.orc_scan_frames_mt.restype = None
+        L.orc_select_range.argtypes = [vp, vp, u32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]
+        L.orc_select_range.restype = u32
+        L.orc_select_pipeline.argtypes = [vp, vp, u32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp]
+        L.orc_select_pipeline.restype = u32
         L.orc_merge_timestamps.argtypes = [vp, u32]
         L.orc_merge_timestamps.restype = u32
         L.orc_build_segments.argtypes = [vp, u32, C.c_double, C.c_double, vp]
@@ -125,3 +129,16 @@ def video_tail(pts, flags, duration, max_gap, padding, min_savings_pct):
     res = OrcResult()
     lib().orc_video_tail(pts.ctypes.data, flags.ctypes.data, n, duration, max_gap, padding, min_savings_pct, segs.ctypes.data, C.byref(res))
     return segs[: res.n_segments].copy(), res
+
+
+def select_pipeline(pts_ticks, is_key, time_base, video_fps, target_fps, duration, chunk_sec):
+    """Frame indices the reference's pipeline hands to check_frame (chunk order)."""
+    pts_ticks = np.ascontiguousarray(pts_ticks, dtype=np.int64)
+    is_key = np.ascontiguousarray(is_key, dtype=np.uint8)
+    n = len(pts_ticks)
+    n_chunks = int(np.ceil(duration / chunk_sec)) + 2
+    out = np.zeros(max(n, 1) * 1 + 8, dtype=np.uint32)
+    k = lib().orc_select_pipeline(pts_ticks.ctypes.data, is_key.ctypes.data, n, time_base, video_fps, target_fps, duration,
+                                  chunk_sec, out.ctypes.data)
+    assert k <= n
+    return out[:k].copy()

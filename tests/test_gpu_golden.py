@@ -12,12 +12,18 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(GOLDEN))
 def test_gpu_matches_reference_outputs(name):
     c, e = cases()[name], expected(name)
+    # host-side frame selection (motion_scanner.cpp:303-371) is input preparation here; the C++ host
+    # mirror's own selection is checked in test_host_cli.py
+    cnt1, _, recs1, pts1 = c.subset(c.selected(chunked=False))
+    cnt2, _, recs2, pts2 = c.subset(c.selected(chunked=True))
     with ms.Context(0, c.params) as ctx:
         ctx.video_open(1, c.width, c.height)
-        ctx.submit(1, c.pts, c.cnt, c.recs if len(c.recs) else None)
-        flags, counts = ctx.collect(1)
-        job, res = ctx.segments(1, e["duration"])
-    assert c.pts[flags.astype(bool)].tobytes() == e["ts"].tobytes()
+        ctx.submit(1, pts1, cnt1, recs1 if len(recs1) else None)
+        flags1, _ = ctx.collect(1)
+        ctx.video_open(2, c.width, c.height)  # frames arrive in chunk order, as the pipeline's workers deliver them
+        ctx.submit(2, pts2, cnt2, recs2 if len(recs2) else None)
+        job, res = ctx.segments(2, e["duration"])
+    assert pts1[flags1.astype(bool)].tobytes() == e["ts"].tobytes()
     assert res.decision == e["decision"]
     assert np.stack([job["start"], job["end"]], 1).reshape(-1, 2).tobytes() == e["segs"].tobytes()
     if res.decision != ms.NO_MOTION:

@@ -30,9 +30,9 @@ def write_case(c, path):
                      tb_num=c.tb[0], tb_den=c.tb[1], duration_us=c.duration_us)
 
 
-def run_cli(args, params, chunk_sec=None, threads=None, extra_env=None):
+def run_cli(args, params, chunk_sec=None, threads=None, extra_env=None, target_fps=None):
     env = dict(os.environ)
-    env.update(ref_runner.env_for(params, chunk_sec))
+    env.update(ref_runner.env_for(params, chunk_sec, target_fps))
     if threads:
         env["THREADS_PER_STREAM"] = str(threads)
     env.update(extra_env or {})
@@ -65,13 +65,15 @@ def test_cli_refuses_without_gpu(have_gpu):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["kat_seg_S1", "kat_seg_S4", "kat_seg_S5", "kat_seg_S7", "clip60s_1080p_config0",
                                   "batchclip_seed100", "batchclip_seed101", "dense_4k_24f", "rand_params_0", "rand_params_5",
-                                  "rand_params_7"])
+                                  "rand_params_7", "skip_tfps10_chunk10", "skip_tfps7_chunk2p5", "skip_tfps4_chunk7",
+                                  "skip_tfps12p5_720p"])
 def test_cli_single_file_matches_reference_pipeline(name):
     c, e = cases()[name], expected(name)
     with tempfile.TemporaryDirectory() as d:
         path, out = Path(d) / "in.mvs", Path(d) / "out.mp4"
         write_case(c, path)
-        r = run_cli(["--print-segments", str(path), str(out)], c.params, chunk_sec=c.chunk_sec, threads=c.threads)
+        r = run_cli(["--print-segments", str(path), str(out)], c.params, chunk_sec=c.chunk_sec, threads=c.threads,
+                    target_fps=c.target_fps)
         assert r.returncode == 0, r.stdout + r.stderr
         res, segs = parse(r.stdout)
         concat = Path(str(out) + ".concat.txt")

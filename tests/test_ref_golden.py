@@ -56,13 +56,20 @@ def test_oracle_matches_reference_outputs(name):
     p = c.params
     gw, gh, m = orc.geometry(c.width, c.height, p.block_size, p.block_shift, p.vertical_mask)
     cfg = orc.make_cfg(p, gw, gh, m)
-    flags_ee, _ = orc.scan_frames(cfg, c.recs, c.off, early_exit=True)
-    flags_fc, counts = orc.scan_frames(cfg, c.recs, c.off, early_exit=False)
+    # leg 1: one scan_range(0, duration): frame selection (:303-371) + check_frame (:217-295)
+    sel1 = c.selected(chunked=False)
+    cnt1, off1, recs1, pts1 = c.subset(sel1)
+    flags_ee, _ = orc.scan_frames(cfg, recs1, off1, early_exit=True)
+    flags_fc, counts = orc.scan_frames(cfg, recs1, off1, early_exit=False)
     assert np.array_equal(flags_ee, flags_fc)
-    # timestamps with motion, exactly as scan_range returned them (motion_scanner.cpp:382-383)
-    ts = c.pts[flags_ee.astype(bool)]
-    assert ts.tobytes() == e["ts"].tobytes()
-    segs, res = orc.video_tail(c.pts, flags_ee, e["duration"], p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+    assert pts1[flags_ee.astype(bool)].tobytes() == e["ts"].tobytes()  # exactly what scan_range returned (:382-383)
+    # leg 2: the chunked pipeline → FFmpegJob
+    sel2 = c.selected(chunked=True)
+    cnt2, off2, recs2, pts2 = c.subset(sel2)
+    flags2, _ = orc.scan_frames(cfg, recs2, off2, early_exit=True)
+    if not c.target_fps:
+        assert np.array_equal(np.sort(sel1), np.sort(sel2))  # without skipping, chunking selects the same frames
+    segs, res = orc.video_tail(pts2, flags2, e["duration"], p.max_gap_sec, p.padding_sec, p.min_savings_pct)
     assert res.decision == e["decision"]
     assert job_segments(segs, res, e["duration"]).tobytes() == e["segs"].tobytes()
     if res.decision != 0:  # no-motion returns before the savings are computed (pipeline.cpp:308-319)
@@ -81,14 +88,14 @@ def test_kat_table_agrees_with_reference_flags():
 
 
 @pytest.mark.skipif(not ref_runner.available(), reason="oracle/_ref/ref_scan not built (needs /root/reference)")
-@pytest.mark.parametrize("name", ["kat_frames_0", "kat_seg_S4", "batchclip_seed100", "rand_params_5"])
+@pytest.mark.parametrize("name", ["kat_frames_0", "kat_seg_S4", "batchclip_seed100", "rand_params_5", "skip_tfps7_chunk2p5"])
 def test_live_reference_reproduces_fixture(name):
     c, e = cases()[name], expected(name)
     with tempfile.TemporaryDirectory() as d:
         path = Path(d) / "x.mvs"
         mvs_io.write_mvs(path, c.width, c.height, c.fps[0], c.fps[1], c.ticks, c.cnt, c.recs, has_mvs=c.has_mvs,
                          tb_num=c.tb[0], tb_den=c.tb[1], duration_us=c.duration_us)
-        r = ref_runner.run(path, c.params, threads=c.threads, chunk_sec=c.chunk_sec)
+        r = ref_runner.run(path, c.params, threads=c.threads, chunk_sec=c.chunk_sec, target_fps=c.target_fps)
     assert r["ts"].tobytes() == e["ts"].tobytes()
     assert r["segs"].tobytes() == e["segs"].tobytes()
     assert r["decision"] == e["decision"] and r["saved_pct"] == e["saved_pct"]
