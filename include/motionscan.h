@@ -83,6 +83,8 @@ typedef struct mscan_params {
   int32_t vectors_needed;  /* VECTORS_NEEDED   (2) — wrapped to uint8 like config.hpp:75 */
   int32_t clusters_needed; /* CLUSTERS_NEEDED  (2)                                     */
   float vertical_mask;     /* VERTICAL_MASK    (0.05f), float32 like config.hpp:87     */
+  int32_t adjacency;       /* CLUSTER_ADJACENCY: 4 = the reference (motion_scanner.cpp:284-286); 8 adds the
+                              diagonals — an extension outside the parity contract. 0 is read as 4. */
   double max_gap_sec;      /* MAX_GAP_SEC      (5.0)                                   */
   double padding_sec;      /* PADDING_SEC      (0.5)                                   */
   double min_savings_pct;  /* MIN_SAVINGS_PCT  (5.0)                                   */

@@ -64,6 +64,9 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
   return m;
 }
 
+// kGlobalCnt: the vote counters of grids too large for shared memory (8K/16K video) live in a
+// per-CTA slice of a zero-initialised global scratch (L2-resident); everything else is identical.
+template <bool kGlobalCnt>
 __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t stages = a.stages;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
   TileDesc* desc = reinterpret_cast<TileDesc*>(ring + (size_t)stages * kTileBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(desc + stages);  // full[stages], empty[stages]
   uint32_t* bits = reinterpret_cast<uint32_t*>(bars + 2 * stages);
-  uint32_t* cnt = bits + 2 * a.max_bit_words;
+  uint32_t* cnt = kGlobalCnt ? a.cnt_scratch + (size_t)blockIdx.x * a.max_cells : bits + 2 * a.max_bit_words;
 
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
     }
     mbar_fence_init();
   }
-  for (uint32_t i = tid; i < a.max_cells; i += kThreads) cnt[i] = 0;
+  if (!kGlobalCnt)  // the global scratch is zero on entry and every epilogue leaves it zero
+    for (uint32_t i = tid; i < a.max_cells; i += kThreads) cnt[i] = 0;
   __syncthreads();
 
   if (warp == 0) {
@@ -213,7 +217,9 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
               uint32_t c = 0;
               const bool valid = x < gw;
               if (valid) {
-                c = cnt[y * gw + x];
+                // global counters are voted with L2 atomics: read them past L1 (a plain load could
+                // return this SM's stale line from the previous frame)
+                c = kGlobalCnt ? __ldcg(&cnt[y * gw + x]) : cnt[y * gw + x];
                 cnt[y * gw + x] = 0;
               }
               const uint32_t word = __ballot_sync(0xffffffffu, valid && c >= vec_need);  // :282
@@ -234,7 +240,14 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
                 const uint32_t Rw = (w + 1 < wpr) ? brow[y * wpr + w + 1] : 0u;
                 const uint32_t U = y ? brow[(y - 1) * wpr + w] : 0u;                       // :286 idx-gw
                 const uint32_t D = (y + 1 < (uint32_t)gh) ? brow[(y + 1) * wpr + w] : 0u;  // :286 idx+gw
-                const uint32_t nb = (A << 1) | (Lw >> 31) | (A >> 1) | (Rw << 31) | U | D;  // :284-286
+                uint32_t nb = (A << 1) | (Lw >> 31) | (A >> 1) | (Rw << 31) | U | D;  // :284-286
+                if (a.adj8) {  // extension (not in the reference): diagonal neighbours too
+                  const uint32_t UL = (y && w) ? brow[(y - 1) * wpr + w - 1] : 0u;
+                  const uint32_t UR = (y && w + 1 < wpr) ? brow[(y - 1) * wpr + w + 1] : 0u;
+                  const uint32_t DL = (y + 1 < (uint32_t)gh && w) ? brow[(y + 1) * wpr + w - 1] : 0u;
+                  const uint32_t DR = (y + 1 < (uint32_t)gh && w + 1 < wpr) ? brow[(y + 1) * wpr + w + 1] : 0u;
+                  nb |= (U << 1) | (UL >> 31) | (U >> 1) | (UR << 31) | (D << 1) | (DL >> 31) | (D >> 1) | (DR << 31);
+                }
                 // centre columns are 1 .. gw-2 (:280)
                 uint32_t mask = 0xFFFFFFFFu;
                 if (w == 0) mask &= ~1u;
@@ -272,40 +285,52 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
 
 constexpr uint32_t kSmemReserve = 1024;  // per-CTA driver reservation
 
-uint32_t smem_for(uint32_t stages, uint32_t max_cells, uint32_t max_bit_words) {
+uint32_t smem_for(uint32_t stages, uint32_t cells_in_smem, uint32_t max_bit_words) {
   return stages * (uint32_t)kTileBytes + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
-         2 * max_bit_words * 4u + max_cells * 4u + 128u;
+         2 * max_bit_words * 4u + cells_in_smem * 4u + 128u;
 }
 
 }  // namespace
 
 bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan) {
   const uint32_t sm_total = 228u * 1024u;
-  // prefer 2 CTAs/SM with >= 3 stages, else 1 CTA/SM with as deep a ring as fits (<= 6)
-  for (uint32_t ctas = 2; ctas >= 1; --ctas) {
-    for (uint32_t st = 6; st >= 2; --st) {
-      const uint32_t need = smem_for(st, max_cells, max_bit_words);
-      if (need > smem_optin) continue;
-      if (ctas * (need + kSmemReserve) > sm_total) continue;
-      if (ctas == 2 && st < 3) continue;
-      plan->stages = (ctas == 2 && st > 4) ? 4 : st;
-      plan->smem_bytes = smem_for(plan->stages, max_cells, max_bit_words);
-      plan->ctas_per_sm = ctas;
-      return true;
+  // prefer 2 CTAs/SM with >= 3 stages, else 1 CTA/SM with as deep a ring as fits (<= 6); if the
+  // counters do not fit at all they move to global memory
+  for (int global_cnt = 0; global_cnt <= 1; ++global_cnt) {
+    const uint32_t cells = global_cnt ? 0u : max_cells;
+    for (uint32_t ctas = global_cnt ? 1 : 2; ctas >= 1; --ctas) {  // global counters: 1 CTA/SM bounds the scratch
+      for (uint32_t st = 6; st >= 2; --st) {
+        const uint32_t need = smem_for(st, cells, max_bit_words);
+        if (need > smem_optin) continue;
+        if (ctas * (need + kSmemReserve) > sm_total) continue;
+        if (ctas == 2 && st < 3) continue;
+        plan->stages = (ctas == 2 && st > 4) ? 4 : st;
+        plan->smem_bytes = smem_for(plan->stages, cells, max_bit_words);
+        plan->ctas_per_sm = ctas;
+        plan->global_cnt = (uint32_t)global_cnt;
+        return true;
+      }
     }
   }
   return false;
 }
 
 cudaError_t scan_configure(uint32_t smem_optin) {
-  return cudaFuncSetAttribute(ka_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+  cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ka_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+}
+
+uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames) {
+  const uint32_t grid = (uint32_t)num_sms * plan.ctas_per_sm;
+  return grid > n_frames ? n_frames : grid;
 }
 
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
-  uint32_t grid = (uint32_t)num_sms * plan.ctas_per_sm;
-  if (grid > a.n_frames) grid = a.n_frames;
-  ka_scan_kernel<<<grid, kThreads, plan.smem_bytes, st>>>(a);
+  const uint32_t grid = scan_grid(plan, num_sms, a.n_frames);
+  if (plan.global_cnt) ka_scan_kernel<true><<<grid, kThreads, plan.smem_bytes, st>>>(a);
+  else ka_scan_kernel<false><<<grid, kThreads, plan.smem_bytes, st>>>(a);
   return cudaGetLastError();
 }
 

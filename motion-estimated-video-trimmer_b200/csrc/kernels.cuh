@@ -32,19 +32,23 @@ struct ScanArgs {
   uint32_t vec_need;           // uint8 VECTORS_NEEDED
   uint32_t clust_need;         // max(1, CLUSTERS_NEEDED)
   uint32_t stages;             // ring depth
-  uint32_t max_cells;          // counters in shared memory
+  uint32_t max_cells;          // vote counters per CTA (shared memory, or a slice of cnt_scratch)
   uint32_t max_bit_words;      // words per bit-row buffer
+  uint32_t adj8;               // extension: 8-neighbour clusters (reference is 4-neighbour only)
+  uint32_t* cnt_scratch;       // zeroed global scratch, grid × max_cells, only when plan.global_cnt
 };
 
 struct ScanPlan {
   uint32_t stages;
   uint32_t smem_bytes;
   uint32_t ctas_per_sm;
+  uint32_t global_cnt;  // counters do not fit shared memory: use the global scratch
 };
 
 // Chooses ring depth / occupancy for the largest geometry; false if it cannot fit.
 bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan);
 cudaError_t scan_configure(uint32_t smem_optin);
+uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames);
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st);
 
 // ---- K-C: compaction + sort/unique + gap merge + savings + decision (pipeline.cpp:297-404)

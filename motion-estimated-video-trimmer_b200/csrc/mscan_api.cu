@@ -103,6 +103,9 @@ struct mscan_ctx {
 
   uint32_t* d_work = nullptr;  // kWorkSlots × {next, done}
   uint32_t work_rr = 0;
+  uint32_t* d_cnt_scratch = nullptr;  // global vote counters for grids beyond shared memory (zeroed)
+  uint64_t cnt_scratch_elems = 0;
+  uint32_t adj8 = 0;
 
   cudaStream_t main_stream = nullptr;
   std::map<uint32_t, Video> videos;
@@ -217,6 +220,29 @@ void drain_events(mscan_ctx* c) {
 int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaStream_t st, uint64_t n_recs) {
   ScanArgs a = args_in;
   a.work = c->d_work + 2 * (c->work_rr++ % kWorkSlots);
+  a.adj8 = c->adj8;
+  a.cnt_scratch = nullptr;
+  if (plan.global_cnt) {
+    // one scratch per context: launches that need it are serialised behind each other
+    const uint64_t need = (uint64_t)c->num_sms * plan.ctas_per_sm * a.max_cells;
+    if (need * sizeof(uint32_t) > (16ull << 30))
+      return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells needs more than 16 GiB of counter scratch", a.max_cells);
+    if (need > c->cnt_scratch_elems) {
+      CU(cudaDeviceSynchronize());
+      cudaFree(c->d_cnt_scratch);
+      c->d_cnt_scratch = nullptr;
+      c->cnt_scratch_elems = 0;
+      if (cudaMalloc((void**)&c->d_cnt_scratch, need * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, MSCAN_ERR_NOMEM, "cannot allocate %llu bytes of vote-counter scratch", (unsigned long long)(need * 4));
+      }
+      CU(cudaMemset(c->d_cnt_scratch, 0, need * sizeof(uint32_t)));
+      c->cnt_scratch_elems = need;
+    } else {
+      CU(cudaDeviceSynchronize());
+    }
+    a.cnt_scratch = c->d_cnt_scratch;
+  }
   EvPair ev{};
   if (c->profiling) {
     ev = get_events(c, 0);
@@ -308,7 +334,9 @@ int sync_scans_locked(mscan_ctx* c) {
 int replan(mscan_ctx* c) {
   ScanPlan p;
   if (!scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, &p))
-    return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells does not fit shared memory", c->max_cells);
+    return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells: bit-rows do not fit shared memory", c->max_cells);
+  if (p.global_cnt && (uint64_t)c->num_sms * p.ctas_per_sm * c->max_cells * sizeof(uint32_t) > (16ull << 30))
+    return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells needs more than 16 GiB of counter scratch", c->max_cells);
   c->plan = p;
   return MSCAN_OK;
 }
@@ -411,6 +439,7 @@ int mscan_params_default(mscan_params* p) {
   p->vectors_needed = 2;      // :75
   p->clusters_needed = 2;     // :81
   p->vertical_mask = 0.05f;   // :87
+  p->adjacency = 4;           // the reference's 4-connectivity (motion_scanner.cpp:284-286)
   p->max_gap_sec = 5.0;       // :93
   p->padding_sec = 0.5;       // :99
   p->min_savings_pct = 5.0;   // :123
@@ -455,6 +484,8 @@ int mscan_params_from_env(mscan_params* p) {
   ok &= env_int("VECTORS_NEEDED", &p->vectors_needed);
   ok &= env_int("CLUSTERS_NEEDED", &p->clusters_needed);
   ok &= env_float("VERTICAL_MASK", &p->vertical_mask);
+  ok &= env_int("CLUSTER_ADJACENCY", &p->adjacency);  // extension knob, not in the reference
+  ok &= (p->adjacency == 4 || p->adjacency == 8);
   ok &= env_double("MAX_GAP_SEC", &p->max_gap_sec);
   ok &= env_double("PADDING_SEC", &p->padding_sec);
   ok &= env_double("MIN_SAVINGS_PCT", &p->min_savings_pct);
@@ -480,6 +511,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   if (!p || !out) return MSCAN_ERR_INVALID;
   *out = nullptr;
   if (p->block_shift < 0 || p->block_shift > 30) return MSCAN_ERR_INVALID;
+  if (p->adjacency != 0 && p->adjacency != 4 && p->adjacency != 8) return MSCAN_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     cudaGetLastError();
@@ -492,6 +524,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   threshold_to_int(p->mv_threshold_sq, &c->ithr, &c->keep_none);
   c->vec_need = (uint32_t)(uint8_t)p->vectors_needed;  // config.hpp:75 static_cast<uint8_t>
   c->clust_need = p->clusters_needed < 1 ? 1u : (uint32_t)p->clusters_needed;
+  c->adj8 = p->adjacency == 8 ? 1u : 0u;
   c->log_cap = max_log_frames ? max_log_frames : (16ull << 20);
   c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (256ull << 20);
   c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
@@ -561,6 +594,7 @@ int mscan_destroy(mscan_ctx* c) {
   }
   cudaFree(c->d_geoms);
   cudaFree(c->d_work);
+  cudaFree(c->d_cnt_scratch);
   cudaFree(c->d_pts);
   cudaFree(c->d_flags);
   cudaFree(c->d_counts);

@@ -37,6 +37,7 @@ class Params(C.Structure):
         ("vectors_needed", C.c_int32),
         ("clusters_needed", C.c_int32),
         ("vertical_mask", C.c_float),
+        ("adjacency", C.c_int32),
         ("max_gap_sec", C.c_double),
         ("padding_sec", C.c_double),
         ("min_savings_pct", C.c_double),

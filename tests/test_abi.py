@@ -41,6 +41,7 @@ def test_defaults_and_env(monkeypatch):
     p = ms.default_params()  # config.hpp:57-123
     assert (p.mv_threshold_sq, p.block_size, p.block_shift, p.vectors_needed, p.clusters_needed) == (16.0, 16, 4, 2, 2)
     assert (p.max_gap_sec, p.padding_sec, p.min_savings_pct) == (5.0, 0.5, 5.0)
+    assert p.adjacency == 4  # the reference's 4-connectivity
     assert p.vertical_mask == np.float32(0.05)
     monkeypatch.setenv("MV_THRESHOLD_SQ", "4.0")
     monkeypatch.setenv("VECTORS_NEEDED", "4")

@@ -296,7 +296,77 @@ def test_errors_are_loud():
         ctx.video_open(1, 1920, 1080)
         with pytest.raises(ms.MscanError):
             ctx.video_open(1, 1920, 1080)  # already open
-        g = ms.Geometry(2000, 2000, 10, 0)  # 4 M cells cannot live in shared memory
+        g = ms.Geometry(32767, 32767, 10, 0)  # 10^9 cells: beyond even the global-memory counter scratch
         with pytest.raises(ms.MscanError) as e:
             ctx.video_open_geometry(2, g)
         assert e.value.code == ms.ERR_UNSUPPORTED
+
+
+def test_large_grid_uses_global_counters():
+    """8K video (480x270 = 129 600 cells) does not fit shared memory: the counters move to a global
+    scratch, results stay bit-exact; a 1080p video interleaved in the same launches is unaffected."""
+    from test_oracle_kats import random_frame
+
+    rng = np.random.default_rng(88)
+    p = kats.env_params(vectors_needed=3)
+    shapes = {1: (7680, 4320), 2: (1920, 1080)}
+    frames = {v: [random_frame(rng, int(rng.integers(1, 20000)), w, h, int(rng.integers(1, 8))) if i % 5 else None
+                  for i in range(30)] for v, (w, h) in shapes.items()}
+    with ms.Context(0, p) as ctx:
+        for v, (w, h) in shapes.items():
+            ctx.video_open(v, w, h)
+        for a in range(0, 30, 6):
+            for v in shapes:
+                fr = frames[v][a : a + 6]
+                cnt = np.array([0 if f is None else len(f) for f in fr], np.uint32)
+                ctx.submit(v, np.arange(a, a + 6) / 30.0, cnt, kats.cat(*[f for f in fr if f is not None]))
+        out = {v: ctx.collect(v) for v in shapes}
+    for v, (w, h) in shapes.items():
+        cfg = cfg_for(p, w, h)
+        for i, f in enumerate(frames[v]):
+            assert out[v][1][i] == orc.full_count(cfg, f), (v, i)
+            assert out[v][0][i] == orc.check_frame(cfg, f), (v, i)
+    assert out[1][0].any()
+
+
+def np_count_adj(p, gw, gh, margin, recs, adj8):
+    """numpy restatement with selectable connectivity (8 = extension, not in the reference)."""
+    tx, ty = recs["dst_x"].astype(np.int64), recs["dst_y"].astype(np.int64)
+    mag = (tx - recs["src_x"].astype(np.int64)) ** 2 + (ty - recs["src_y"].astype(np.int64)) ** 2
+    gx, gy = tx >> p.block_shift, ty >> p.block_shift
+    keep = ~(mag.astype(np.float64) < p.mv_threshold_sq) & (gx >= 0) & (gx < gw) & (gy >= margin) & (gy < gh - margin)
+    grid = np.zeros((gh, gw), np.int64)
+    np.add.at(grid, (gy[keep], gx[keep]), 1)
+    act = grid >= (p.vectors_needed & 0xFF)
+    pad = np.zeros((gh + 2, gw + 2), bool)
+    pad[1:-1, 1:-1] = act
+    nb = pad[1:-1, :-2] | pad[1:-1, 2:] | pad[:-2, 1:-1] | pad[2:, 1:-1]
+    if adj8:
+        nb |= pad[:-2, :-2] | pad[:-2, 2:] | pad[2:, :-2] | pad[2:, 2:]
+    cl = act & nb
+    cl[:, 0] = cl[:, gw - 1] = False
+    cl[:margin, :] = False
+    cl[gh - margin :, :] = False
+    return int(cl.sum())
+
+
+def test_adjacency8_extension():
+    """CLUSTER_ADJACENCY=8 (extension behind a knob, default 4 = reference): K5's diagonal pair becomes a
+    cluster; random frames agree with a numpy restatement; adjacency 4 is unchanged."""
+    from test_oracle_kats import random_frame
+
+    p8 = kats.env_params(adjacency=8)
+    diag = kats.cat(kats.cell(10, 10), kats.cell(11, 11))
+    # word-boundary diagonals: cells (31,20)/(32,21) and (64,30)/(63,31) straddle 32-bit bit-row words
+    edge = kats.cat(kats.cell(31, 20), kats.cell(32, 21), kats.cell(64, 30), kats.cell(63, 31))
+    rng = np.random.default_rng(5)
+    rnd = [random_frame(rng, 4000, kats.W, kats.H, 6) for _ in range(6)]
+    with ms.Context(0, p8) as ctx:
+        f8, c8 = run_frames(ctx, 1, kats.W, kats.H, [diag, edge] + rnd)
+    with ms.Context(0, kats.env_params()) as ctx:
+        f4, c4 = run_frames(ctx, 1, kats.W, kats.H, [diag, edge] + rnd)
+    assert (f4[0], c4[0]) == (0, 0) and (f8[0], c8[0]) == (1, 2)
+    assert c4[1] == 0 and c8[1] == 4
+    for i, r in enumerate(rnd):
+        assert c8[2 + i] == np_count_adj(p8, 120, 68, 3, r, True)
+        assert c4[2 + i] == np_count_adj(p8, 120, 68, 3, r, False)
