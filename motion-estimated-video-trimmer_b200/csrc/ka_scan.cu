@@ -21,6 +21,8 @@
 //     with shfl/ballot so one lane issues one atomic for the run;
 //   * counters are u32 (saturation at 255, :265-266, is unobservable for VECTORS_NEEDED <= 255);
 //   * the epilogue is skipped for frames in which nothing voted (the common CCTV case).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -30,9 +32,8 @@ namespace {
 
 constexpr int kTileRec = 512;                      // records per ring stage
 constexpr int kTileBytes = kTileRec * kRecBytes;   // 20480, multiple of lcm(16,40)=80
-constexpr int kConsWarps = 8;
-constexpr int kCons = kConsWarps * 32;
-constexpr int kThreads = kCons + 32;
+// consumer warps per CTA: 8 when two CTAs share an SM, 16 when only one fits (4K grids: the sweep in
+// tools/ka_sweep.py shows one CTA of 8 consumer warps cannot keep up with HBM)
 constexpr uint32_t kEndFrame = 0xFFFFFFFFu;
 constexpr uint32_t kBarCons = 1;  // named barrier id of the consumer warps
 
@@ -66,8 +67,16 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
 
 // kGlobalCnt: the vote counters of grids too large for shared memory (8K/16K video) live in a
 // per-CTA slice of a zero-initialised global scratch (L2-resident); everything else is identical.
-template <bool kGlobalCnt>
-__global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
+// kCnt16: counters are 16-bit halves of shared-memory words (half the footprint ⇒ a deeper ring for 4K
+// grids). A vote is still one 32-bit atomicAdd on the containing word; a guard stops adding once a
+// half reaches 0x7FFF, and since at most kCons lanes × 32 merged votes can pass the guard concurrently
+// a half never carries into its neighbour. Counts >= 0x7FFF are reported as "many": exact for the
+// active test because VECTORS_NEEDED <= 255.
+template <bool kGlobalCnt, int kConsWarps, bool kCnt16>
+__global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
+  static_assert(!(kGlobalCnt && kCnt16), "global counters are always 32-bit");
+  constexpr int kCons = kConsWarps * 32;
+  constexpr int kThreads = kCons + 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t stages = a.stages;
   unsigned char* ring = smem;
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
     mbar_fence_init();
   }
   if (!kGlobalCnt)  // the global scratch is zero on entry and every epilogue leaves it zero
-    for (uint32_t i = tid; i < a.max_cells; i += kThreads) cnt[i] = 0;
+    for (uint32_t i = tid; i < (kCnt16 ? (a.max_cells + 1) / 2 : a.max_cells); i += kThreads) cnt[i] = 0;
   __syncthreads();
 
   if (warp == 0) {
@@ -192,7 +201,13 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
         if (head && key >= 0) {
           const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
           const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
-          atomicAdd(&cnt[key], next - lane);                               // :265-266
+          if (kCnt16) {
+            uint32_t* w = &cnt[(uint32_t)key >> 1];
+            const uint32_t sh = ((uint32_t)key & 1u) * 16u;
+            if (((*reinterpret_cast<volatile uint32_t*>(w) >> sh) & 0xFFFFu) < 0x7FFFu) atomicAdd(w, (next - lane) << sh);
+          } else {
+            atomicAdd(&cnt[key], next - lane);                             // :265-266
+          }
           voted = true;
         }
       }
@@ -217,10 +232,16 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
               uint32_t c = 0;
               const bool valid = x < gw;
               if (valid) {
-                // global counters are voted with L2 atomics: read them past L1 (a plain load could
-                // return this SM's stale line from the previous frame)
-                c = kGlobalCnt ? __ldcg(&cnt[y * gw + x]) : cnt[y * gw + x];
-                cnt[y * gw + x] = 0;
+                if (kCnt16) {
+                  uint16_t* h = reinterpret_cast<uint16_t*>(cnt) + (y * gw + x);
+                  c = *h;
+                  *h = 0;
+                } else {
+                  // global counters are voted with L2 atomics: read them past L1 (a plain load could
+                  // return this SM's stale line from the previous frame)
+                  c = kGlobalCnt ? __ldcg(&cnt[y * gw + x]) : cnt[y * gw + x];
+                  cnt[y * gw + x] = 0;
+                }
               }
               const uint32_t word = __ballot_sync(0xffffffffu, valid && c >= vec_need);  // :282
               if (lane == 0) brow[(uint32_t)y * wpr + w] = word;
@@ -285,40 +306,76 @@ __global__ void __launch_bounds__(kThreads, 2) ka_scan_kernel(const __grid_const
 
 constexpr uint32_t kSmemReserve = 1024;  // per-CTA driver reservation
 
-uint32_t smem_for(uint32_t stages, uint32_t cells_in_smem, uint32_t max_bit_words) {
+uint32_t smem_for(uint32_t stages, uint32_t counter_bytes, uint32_t max_bit_words) {
   return stages * (uint32_t)kTileBytes + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
-         2 * max_bit_words * 4u + cells_in_smem * 4u + 128u;
+         2 * max_bit_words * 4u + ((counter_bytes + 15u) & ~15u) + 128u;
+}
+
+// Tuning overrides for experiments (tools/ka_sweep.py): MSCAN_KA_CTAS, MSCAN_KA_STAGES, MSCAN_KA_WARPS, MSCAN_KA_CNT16.
+uint32_t env_u32(const char* name) {
+  const char* s = std::getenv(name);
+  return s ? (uint32_t)std::strtoul(s, nullptr, 10) : 0u;
+}
+
+// largest ring depth in [lo, hi] that fits `ctas` CTAs per SM; 0 if none
+uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, uint32_t smem_optin, uint32_t lo, uint32_t hi) {
+  const uint32_t sm_total = 228u * 1024u;
+  for (uint32_t st = hi; st >= lo; --st) {
+    const uint32_t need = smem_for(st, counter_bytes, bit_words);
+    if (need <= smem_optin && ctas * (need + kSmemReserve) <= sm_total) return st;
+  }
+  return 0;
 }
 
 }  // namespace
 
 bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan) {
-  const uint32_t sm_total = 228u * 1024u;
-  // prefer 2 CTAs/SM with >= 3 stages, else 1 CTA/SM with as deep a ring as fits (<= 6); if the
-  // counters do not fit at all they move to global memory
-  for (int global_cnt = 0; global_cnt <= 1; ++global_cnt) {
-    const uint32_t cells = global_cnt ? 0u : max_cells;
-    for (uint32_t ctas = global_cnt ? 1 : 2; ctas >= 1; --ctas) {  // global counters: 1 CTA/SM bounds the scratch
-      for (uint32_t st = 6; st >= 2; --st) {
-        const uint32_t need = smem_for(st, cells, max_bit_words);
-        if (need > smem_optin) continue;
-        if (ctas * (need + kSmemReserve) > sm_total) continue;
-        if (ctas == 2 && st < 3) continue;
-        plan->stages = (ctas == 2 && st > 4) ? 4 : st;
-        plan->smem_bytes = smem_for(plan->stages, cells, max_bit_words);
-        plan->ctas_per_sm = ctas;
-        plan->global_cnt = (uint32_t)global_cnt;
-        return true;
-      }
+  const uint32_t b32 = max_cells * 4u, b16 = ((max_cells + 1u) / 2u) * 4u;
+  auto set = [&](uint32_t ctas, uint32_t st, uint32_t cnt16, uint32_t global_cnt) {
+    plan->stages = st;
+    plan->ctas_per_sm = ctas;
+    plan->cnt16 = cnt16;
+    plan->global_cnt = global_cnt;
+    plan->cons_warps = ctas == 1 ? 16 : 8;
+    plan->smem_bytes = smem_for(st, global_cnt ? 0u : (cnt16 ? b16 : b32), max_bit_words);
+    return true;
+  };
+  const uint32_t want_st = env_u32("MSCAN_KA_STAGES"), want_ctas = env_u32("MSCAN_KA_CTAS");
+  if (want_st >= 2 && want_st <= 10 && want_ctas >= 1 && want_ctas <= 4) {
+    const uint32_t c16 = env_u32("MSCAN_KA_CNT16") ? 1u : 0u;
+    if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st)) {
+      set(want_ctas, want_st, c16, 0);
+      const uint32_t w = env_u32("MSCAN_KA_WARPS");
+      if (w == 8 || (w == 16 && want_ctas == 1)) plan->cons_warps = w;
+      return true;
     }
   }
+  uint32_t st;
+  // 1-4: two CTAs per SM; a 4-stage ring (160 KB in flight per SM) measures ~1.3 % faster than 3 stages
+  // (tools/ka_sweep.py), so 16-bit counters are preferred when they are what makes the 4th stage fit
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4))) return set(2, st, 0, 0);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 4, 4))) return set(2, st, 1, 0);
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 3, 3))) return set(2, st, 0, 0);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 3, 3))) return set(2, st, 1, 0);
+  // 5-7: one CTA per SM with 16 consumer warps and as deep a ring as fits (4K: u16 counters give 7 stages)
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 6, 8))) return set(1, st, 0, 0);
+  if ((st = fit_stages(1, b16, max_bit_words, smem_optin, 2, 8))) return set(1, st, 1, 0);
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 2, 8))) return set(1, st, 0, 0);
+  // 8: counters in global memory (8K and larger)
+  if ((st = fit_stages(1, 0, max_bit_words, smem_optin, 2, 8))) return set(1, st, 0, 1);
   return false;
 }
 
 cudaError_t scan_configure(uint32_t smem_optin) {
-  cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(ka_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+  const int v = (int)smem_optin;
+  const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+  cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, false>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, false>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, true>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, true>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 8, false>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 16, false>, attr, v);
+  return e;
 }
 
 uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames) {
@@ -329,8 +386,18 @@ uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames) {
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
   const uint32_t grid = scan_grid(plan, num_sms, a.n_frames);
-  if (plan.global_cnt) ka_scan_kernel<true><<<grid, kThreads, plan.smem_bytes, st>>>(a);
-  else ka_scan_kernel<false><<<grid, kThreads, plan.smem_bytes, st>>>(a);
+  const bool wide = plan.cons_warps == 16;
+  const uint32_t threads = plan.cons_warps * 32 + 32;
+  if (plan.global_cnt) {
+    if (wide) ka_scan_kernel<true, 16, false><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<true, 8, false><<<grid, threads, plan.smem_bytes, st>>>(a);
+  } else if (plan.cnt16) {
+    if (wide) ka_scan_kernel<false, 16, true><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<false, 8, true><<<grid, threads, plan.smem_bytes, st>>>(a);
+  } else {
+    if (wide) ka_scan_kernel<false, 16, false><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<false, 8, false><<<grid, threads, plan.smem_bytes, st>>>(a);
+  }
   return cudaGetLastError();
 }
 

@@ -43,6 +43,8 @@ struct ScanPlan {
   uint32_t smem_bytes;
   uint32_t ctas_per_sm;
   uint32_t global_cnt;  // counters do not fit shared memory: use the global scratch
+  uint32_t cons_warps;  // 8 (two CTAs per SM) or 16 (one CTA per SM)
+  uint32_t cnt16;       // 16-bit shared-memory counters (half the footprint, guarded against carry)
 };
 
 // Chooses ring depth / occupancy for the largest geometry; false if it cannot fit.

@@ -329,6 +329,21 @@ def test_large_grid_uses_global_counters():
     assert out[1][0].any()
 
 
+def test_4k_u16_counters_saturation_guard():
+    """4K grids use 16-bit shared-memory counters (two per word). 120 000 votes into one cell must not
+    carry into its word-mate: the neighbour cell (same 32-bit word) stays below VECTORS_NEEDED."""
+    p = kats.env_params()
+    heavy = kats.cat(kats.cell(100, 50, 120000), kats.cell(101, 50, 3))   # cells 100/101 of a row share a word
+    pair = kats.cat(kats.cell(100, 50, 70000), kats.cell(101, 50, 70000))
+    lone = kats.cat(kats.cell(101, 60, 90000))                           # odd cell alone: even mate must stay 0
+    cfg = cfg_for(p, 3840, 2160)
+    with ms.Context(0, p) as ctx:
+        flags, counts = run_frames(ctx, 1, 3840, 2160, [heavy, pair, lone, heavy])
+    want = [orc.full_count(cfg, f) for f in (heavy, pair, lone, heavy)]
+    assert want == [0, 2, 0, 0]
+    assert list(counts) == want and list(flags) == [0, 1, 0, 0]
+
+
 def np_count_adj(p, gw, gh, margin, recs, adj8):
     """numpy restatement with selectable connectivity (8 = extension, not in the reference)."""
     tx, ty = recs["dst_x"].astype(np.int64), recs["dst_y"].astype(np.int64)
