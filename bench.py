@@ -367,6 +367,21 @@ def run_gpu(args):
     ctx.d2h(flags, d_flags)
     ctx.d2h(res, d_res)
 
+    # ---- PCIe roofline denominator: pinned H2D copy, 1 GiB, best of 8 -----------------
+    pin = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+    dev = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    pcie_gbs = 0.0
+    with torch.cuda.stream(stream):
+        for _ in range(9):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            dev.copy_(pin, non_blocking=True)
+            b.record(stream)
+            stream.synchronize()
+            pcie_gbs = max(pcie_gbs, (1 << 30) / (a.elapsed_time(b) * 1e-3) / 1e9)
+    del pin, dev
+    pcie_gbs = allmax(pcie_gbs)
+
     # ---- e2e: host-fed through the C ABI ------------------------------------------------------------
     # host-resident sample: the leading frames of the stream, bounded by --e2e-records (~3.6 GB pinned)
     e2e_frames = int(min(max(np.searchsorted(off, np.uint64(int(args.e2e_records)), side="right") - 1, 1), n_frames))
@@ -473,6 +488,9 @@ def run_gpu(args):
                 "frames": e2e_frames,
                 "records": e_rec,
                 "h2d_gbs": est.h2d_bytes / e2e_dt / 1e9,
+                "pcie_peak_gbs": pcie_gbs,
+                "pcie_frac": (est.h2d_bytes / e2e_dt / 1e9) / pcie_gbs if pcie_gbs > 0 else None,
+                "pcie_peak_how": "pinned cudaMemcpyAsync H2D, 1 GiB, best of 9, CUDA events (per GPU)",
                 "launches": e2e_launches,
                 "matches_device_resident": e2e_ok,
                 "how": "mscan_video_open/submit (pinned host records DMA'd in place)/collect/segments_batch/close per step",

@@ -1,0 +1,162 @@
+"""GPU: edge cases and size-independent properties — degenerate knobs, empty inputs, concurrent submits,
+idempotence / batching invariance at a large device-resident size with oracle spot checks."""
+import threading
+import zlib
+
+import numpy as np
+import pytest
+
+import kats
+import motionscan as ms
+import oracle_lib as orc
+from test_gpu_parity import cfg_for, oracle_tail, run_frames
+from test_oracle_kats import random_frame
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("knobs", [
+    dict(mv_threshold_sq=float("nan")),          # every `<` against NaN is false ⇒ all vectors kept
+    dict(mv_threshold_sq=float("inf")),          # nothing is ever kept
+    dict(mv_threshold_sq=-5.0),                  # negative threshold keeps zero-length vectors too
+    dict(mv_threshold_sq=3e9),                   # above INT32_MAX
+    dict(mv_threshold_sq=0.5),                   # fractional: ceil() on the device
+    dict(vectors_needed=0),                      # every cell active (also masked rows, as neighbours)
+    dict(vectors_needed=256),                    # wraps to 0 (config.hpp:75)
+    dict(vectors_needed=260),                    # wraps to 4
+    dict(vectors_needed=255),
+    dict(clusters_needed=0),
+    dict(clusters_needed=-3),
+    dict(clusters_needed=100000),
+    dict(block_size=8, block_shift=3),           # 240x135 grid on 1080p
+    dict(block_size=32, block_shift=5),
+    dict(vertical_mask=0.2),
+    dict(vertical_mask=0.49),                    # 2 live rows on 1080p (margin 33 of 68)
+])
+def test_degenerate_knobs(knobs):
+    p = kats.env_params(**knobs)
+    rng = np.random.default_rng(zlib.crc32(repr(sorted(knobs.items())).encode()))
+    frames = [random_frame(rng, int(rng.integers(1, 5000)), kats.W, kats.H, 4) for _ in range(10)] + [None, kats.cell(10, 10, 300)]
+    cfg = cfg_for(p, kats.W, kats.H)
+    assert cfg.vertical_margin >= 1
+    with ms.Context(0, p) as ctx:
+        flags, counts = run_frames(ctx, 1, kats.W, kats.H, frames)
+    for i, f in enumerate(frames):
+        assert counts[i] == orc.full_count(cfg, f), (knobs, i)
+        assert flags[i] == orc.check_frame(cfg, f), (knobs, i)
+
+
+def test_empty_inputs():
+    p = kats.env_params()
+    with ms.Context(0, p) as ctx:
+        ctx.video_open(1, 1920, 1080)
+        flags, counts = ctx.collect(1)                       # a video nobody submitted to
+        assert len(flags) == 0 and len(counts) == 0
+        segs, res = ctx.segments(1, 60.0)
+        assert res.decision == ms.NO_MOTION and len(segs) == 0
+        assert ctx.submit(1, np.zeros(0), np.zeros(0, np.uint32), None) == 0   # zero frames is a no-op
+        ctx.submit(1, np.arange(5) / 30.0, np.zeros(5, np.uint32), None)       # frames without side data
+        flags, counts = ctx.collect(1)
+        assert not flags.any() and not counts.any() and len(flags) == 5
+        segs, res = ctx.segments(1, 60.0)
+        assert res.decision == ms.NO_MOTION and res.n_motion_frames == 0
+        ctx.video_close(1)
+        segs, off, res = ctx.segments_batch([], [])
+        assert len(segs) == 0 and len(res) == 0
+
+
+def test_concurrent_submits_from_many_threads():
+    """Decode workers of several videos call mscan_submit concurrently (motion_scanner.hpp:8-13: one scanner
+    per thread); chunks of one video may arrive in any order — K-C sorts them like pipeline.cpp:302-304."""
+    p = kats.env_params()
+    specs = {v: ms.synth_preset(0, 200 + v) for v in range(4)}
+    data = {v: ms.synth_host(s, 0, 240) for v, s in specs.items()}
+    errors = []
+    with ms.Context(0, p, 0, 16 << 20) as ctx:
+        for v, s in specs.items():
+            ctx.video_open(v, s.width, s.height)
+
+        def worker(v, chunks):
+            try:
+                cnt, off, recs, pts = data[v]
+                for a in chunks:
+                    b = a + 30
+                    ctx.submit(v, pts[a:b], cnt[a:b], recs[int(off[a]) : int(off[b])])
+            except Exception as e:  # pragma: no cover
+                errors.append(e)
+
+        threads = []
+        for v in specs:  # two workers per video, interleaved chunk order
+            threads.append(threading.Thread(target=worker, args=(v, [0, 60, 120, 180])))
+            threads.append(threading.Thread(target=worker, args=(v, [210, 150, 90, 30])))
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors
+        segs, soff, res = ctx.segments_batch(list(specs), [8.0] * 4)
+        motion = {v: ctx.motion_segments(v, 8.0) for v in specs}
+        collected = {v: ctx.collect(v) for v in specs}
+    for i, v in enumerate(specs):
+        cnt, off, recs, pts = data[v]
+        of, oc = orc.scan_frames(cfg_for(p, 1920, 1080), recs, off, threads=4)
+        assert collected[v][0].sum() == of.sum() and collected[v][1].sum() == oc.sum()  # same frames, arrival order differs
+        osegs, ores = oracle_tail(p, pts, of, 8.0)
+        assert res["decision"][i] == ores.decision and res["n_motion_frames"][i] == ores.n_motion_frames
+        assert motion[v][0].tobytes() == osegs.tobytes()
+        assert np.float64(res["saved_pct"][i]).tobytes() == np.float64(ores.saved_pct).tobytes()
+
+
+def test_fullsize_properties_device_resident():
+    """~2x10^8 records on the device (8 GB): scanning is idempotent, independent of how the frames are split
+    into launches, and agrees with the oracle on randomly chosen frames regenerated on the host."""
+    p = kats.env_params()
+    spec = ms.synth_preset(4, 5)
+    n = 20000
+    with ms.Context(0, p) as ctx:
+        d_cnt, d_off = ctx.dev_alloc(4 * n), ctx.dev_alloc(8 * (n + 1))
+        ctx.synth_counts(spec, 0, n, d_cnt)
+        ctx.offsets_from_counts(d_cnt, n, d_off)
+        ctx.sync()
+        off = np.zeros(n + 1, np.uint64)
+        ctx.d2h(off, d_off)
+        n_rec = int(off[-1])
+        assert n_rec > 1.9e8
+        d_recs, d_pts = ctx.dev_alloc(40 * n_rec + 256), ctx.dev_alloc(8 * n)
+        ctx.synth_fill(spec, 0, n, d_off, d_recs, d_pts)
+        geom = ms.geometry_from_dims(p, spec.width, spec.height)
+        outs = []
+        for rep in range(2):  # idempotence
+            d_f, d_c = ctx.dev_alloc(n), ctx.dev_alloc(4 * n)
+            ctx.scan_device(d_recs, d_off, None, [geom], n, d_f, d_c)
+            ctx.sync()
+            f, c = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+            ctx.d2h(f, d_f)
+            ctx.d2h(c, d_c)
+            outs.append((f, c))
+            ctx.dev_free(d_f)
+            ctx.dev_free(d_c)
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+        # the same frames in three unequal launches (offsets shifted: each launch sees a sub-range of rec_off)
+        d_f, d_c = ctx.dev_alloc(n), ctx.dev_alloc(4 * n)
+        for a, b in [(0, 7), (7, 12345), (12345, n)]:
+            ctx.scan_device(d_recs, d_off + 8 * a, None, [geom], b - a, d_f + a, d_c + 4 * a)
+        ctx.sync()
+        f3, c3 = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        ctx.d2h(f3, d_f)
+        ctx.d2h(c3, d_c)
+        assert np.array_equal(f3, outs[0][0]) and np.array_equal(c3, outs[0][1])
+        for d in (d_cnt, d_off, d_recs, d_pts, d_f, d_c):
+            ctx.dev_free(d)
+    flags, counts = outs[0]
+    assert 0 < flags.sum() < n and counts.max() > 10
+    assert not flags[::30].any()  # I-frames (no records) are never active
+    # oracle spot checks: 200 random frames + the busiest ones, regenerated on the host
+    rng = np.random.default_rng(1)
+    pick = np.unique(np.concatenate([rng.integers(0, n, 200), np.argsort(counts)[-20:]]))
+    cfg = cfg_for(p, spec.width, spec.height)
+    for i in pick:
+        cnt1, off1, recs1, _ = ms.synth_host(spec, int(i), 1, n_threads=1)
+        assert int(cnt1[0]) == int(off[i + 1] - off[i])
+        assert counts[i] == orc.full_count(cfg, recs1 if len(recs1) else None), i
+        assert flags[i] == orc.check_frame(cfg, recs1 if len(recs1) else None), i
