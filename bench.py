@@ -65,6 +65,24 @@ def measured_traffic(n_rec, n_frames):
     return best
 
 
+def bind_to_gpu_numa(index: int):
+    """Best effort: restrict this rank to the CPUs NVML reports as local to its GPU (multi-rank runs only)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------ clocks ------
 class ClockSampler:
     """Samples SM clock + throttle reasons during the timed region (pynvml, else nvidia-smi)."""
@@ -283,6 +301,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the motion-scan path has no CPU fallback")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa(local)  # pinned staging is then allocated on the GPU's own NUMA node
     D = Dist("nccl", torch.device("cuda", local))
     world, rank = D.world, D.rank
     barrier, allmax, allsum = D.barrier, D.allmax, D.allsum

@@ -155,9 +155,10 @@ int mscan_video_open(mscan_ctx* ctx, uint32_t video_id, int width, int height);
 int mscan_video_open_geometry(mscan_ctx* ctx, uint32_t video_id, const mscan_geometry* g);
 /* Append n_frames frames of one video. recs holds the frames' records back to back in FFmpeg's
  * native layout; rec_count[i] == 0 means "no MV side data" (motion_scanner.cpp:219-221).
- * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / cudaHostRegister) it is DMA'd
- * in place and must stay valid until mscan_flush/mscan_collect returns; pageable memory is
- * copied into the library's pinned ring before the call returns.
+ * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / mscan_host_register /
+ * cudaHostRegister) it is DMA'd in place and must stay valid until the copy has completed, i.e. until
+ * mscan_host_fence, mscan_sync, mscan_collect* or mscan_segments* returns (mscan_flush only enqueues);
+ * pageable memory is copied into the library's pinned ring before the call returns.
  * first_frame_out (may be NULL): index, in the video's submission order, of this call's first
  * frame — what a chunk worker needs to read back its own frames with mscan_collect_range. */
 int mscan_submit(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
@@ -186,6 +187,14 @@ int mscan_video_close(mscan_ctx* ctx, uint32_t video_id);
 /* pinned host memory for zero-copy submit */
 int mscan_host_alloc(mscan_ctx* ctx, size_t bytes, void** p_out);
 int mscan_host_free(mscan_ctx* ctx, void* p);
+/* Pin memory the caller already owns (e.g. the mmap of an MV stream file; read_only for PROT_READ
+ * mappings) so mscan_submit DMAs it in place. MSCAN_ERR_CUDA if the platform refuses; the caller then
+ * simply submits the pageable pointer. */
+int mscan_host_register(mscan_ctx* ctx, void* p, size_t bytes, int read_only);
+int mscan_host_unregister(mscan_ctx* ctx, void* p);
+/* Launches what is staged and blocks until every record submitted so far has been copied off the host
+ * (kernels may still be running): after it returns, pinned source buffers can be reused. */
+int mscan_host_fence(mscan_ctx* ctx);
 
 /* ---- device-resident path (caller-owned device buffers) ---------------- */
 int mscan_dev_alloc(mscan_ctx* ctx, size_t bytes, void** d_out);

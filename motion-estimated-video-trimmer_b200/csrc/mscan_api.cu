@@ -55,6 +55,7 @@ struct Slab {
   double* h_pts = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t copied = nullptr;  // recorded after the slab's last H2D copy (mscan_host_fence)
   bool in_flight = false;
   uint64_t bytes = 0;
   uint64_t recs = 0;
@@ -277,6 +278,7 @@ int launch_slab(mscan_ctx* c, Slab& s) {
   CU(cudaMemcpyAsync(s.d_geom, s.h_geom, sizeof(uint32_t) * s.frames, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(c->d_pts + s.log_base, s.h_pts, sizeof(double) * s.frames, cudaMemcpyHostToDevice, s.stream));
   c->stats.h2d_bytes += sizeof(uint64_t) * (s.frames + 1) + 12ull * s.frames;
+  CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of this slab precedes this point
   ScanArgs a = base_args(c);
   a.recs = s.d_recs;
   a.rec_off = s.d_rec_off;
@@ -557,6 +559,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   for (auto& s : c->slabs) {
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CUB_(cudaMalloc((void**)&s.d_recs, c->slab_bytes + 256));
     CUB_(cudaMalloc((void**)&s.d_rec_off, sizeof(uint64_t) * (c->slab_frames + 1)));
     CUB_(cudaMalloc((void**)&s.d_geom, sizeof(uint32_t) * c->slab_frames));
@@ -590,6 +593,7 @@ int mscan_destroy(mscan_ctx* c) {
     if (s.h_geom) cudaFreeHost(s.h_geom);
     if (s.h_pts) cudaFreeHost(s.h_pts);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.copied) cudaEventDestroy(s.copied);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   cudaFree(c->d_geoms);
@@ -1025,6 +1029,38 @@ int mscan_host_alloc(mscan_ctx* c, size_t bytes, void** p) {
 int mscan_host_free(mscan_ctx* c, void* p) {
   if (!c) return MSCAN_ERR_INVALID;
   if (p) CU(cudaFreeHost(p));
+  return MSCAN_OK;
+}
+
+int mscan_host_register(mscan_ctx* c, void* p, size_t bytes, int read_only) {
+  if (!c || !p || !bytes) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  unsigned flags = cudaHostRegisterPortable;
+  if (read_only) flags |= cudaHostRegisterReadOnly;
+  const cudaError_t e = cudaHostRegister(p, bytes, flags);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, MSCAN_ERR_CUDA, "cudaHostRegister(%zu bytes%s) refused: %s", bytes, read_only ? ", read-only" : "",
+                cudaGetErrorString(e));
+  }
+  return MSCAN_OK;
+}
+
+int mscan_host_unregister(mscan_ctx* c, void* p) {
+  if (!c || !p) return MSCAN_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaHostUnregister(p));
+  return MSCAN_OK;
+}
+
+int mscan_host_fence(mscan_ctx* c) {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  int rc = flush_locked(c);  // the open slab's copies get their `copied` event at launch
+  if (rc) return rc;
+  for (auto& s : c->slabs)
+    if (s.in_flight) CU(cudaEventSynchronize(s.copied));
   return MSCAN_OK;
 }
 

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <filesystem>
 #include <mutex>
 #include <thread>
@@ -67,12 +68,28 @@ int ProcessingPipeline::run() {
     logf(stream_id_, "[ERROR] ", "stream has no duration");
     return 1;
   }
+  // Pin the mapped stream so mscan_submit DMAs records straight out of the page cache; if the platform
+  // refuses (or MOTION_TRIM_NO_PIN is set) submits fall back to the library's pinned staging copy.
+  bool registered = false;
+  if (!std::getenv("MOTION_TRIM_NO_PIN"))
+    registered = mscan_host_register(gpu, const_cast<uint8_t*>(file_buffer_.data()), file_buffer_.size(), 1) == MSCAN_OK;
+  struct Unpin {
+    mscan_ctx* g;
+    const uint8_t* p;
+    bool on;
+    ~Unpin() {
+      if (!on) return;
+      mscan_host_fence(g);  // no DMA may still be reading the mapping
+      mscan_host_unregister(g, const_cast<uint8_t*>(p));
+    }
+  } unpin{gpu, file_buffer_.data(), registered};
   if (mscan_video_open(gpu, video_id, width, height) != MSCAN_OK) {
     logf(stream_id_, "[ERROR] ", std::string("mscan_video_open: ") + mscan_last_error(gpu));
     return 1;
   }
   char buf[160];
-  std::snprintf(buf, sizeof buf, "Duration: %.2fs (%.0f frames @ %.1ffps) on GPU %d", duration_, duration_ * fps, fps, gpu_index_);
+  std::snprintf(buf, sizeof buf, "Duration: %.2fs (%.0f frames @ %.1ffps) on GPU %d%s", duration_, duration_ * fps, fps, gpu_index_,
+                registered ? ", input pinned for in-place DMA" : "");
   logf(stream_id_, "[INFO] ", buf);
 
   // ---- chunk queue + workers (the workers are the decode front-end; here they walk the MVS index)

@@ -140,6 +140,9 @@ SYMBOLS = {
     "mscan_video_close": (_i, [_vp, _u32]),
     "mscan_host_alloc": (_i, [_vp, C.c_size_t, _P(_vp)]),
     "mscan_host_free": (_i, [_vp, _vp]),
+    "mscan_host_register": (_i, [_vp, _vp, C.c_size_t, _i]),
+    "mscan_host_unregister": (_i, [_vp, _vp]),
+    "mscan_host_fence": (_i, [_vp]),
     "mscan_dev_alloc": (_i, [_vp, C.c_size_t, _P(_vp)]),
     "mscan_dev_free": (_i, [_vp, _vp]),
     "mscan_memcpy_h2d": (_i, [_vp, _vp, _vp, C.c_size_t]),
@@ -347,6 +350,15 @@ class Context:
 
     def host_free(self, p: int):
         self._ck(self.L.mscan_host_free(self.h, p))
+
+    def host_register(self, a: np.ndarray, read_only: bool = False):
+        self._ck(self.L.mscan_host_register(self.h, a.ctypes.data, a.nbytes, int(read_only)))
+
+    def host_unregister(self, a: np.ndarray):
+        self._ck(self.L.mscan_host_unregister(self.h, a.ctypes.data))
+
+    def host_fence(self):
+        self._ck(self.L.mscan_host_fence(self.h))
 
     def pinned_array(self, shape, dtype):
         """numpy view over pinned host memory (freed with host_free(arr.ctypes.data))."""

@@ -160,3 +160,32 @@ def test_fullsize_properties_device_resident():
         assert int(cnt1[0]) == int(off[i + 1] - off[i])
         assert counts[i] == orc.full_count(cfg, recs1 if len(recs1) else None), i
         assert flags[i] == orc.check_frame(cfg, recs1 if len(recs1) else None), i
+
+
+def test_host_register_and_fence_allow_buffer_reuse():
+    """A caller-owned buffer pinned with mscan_host_register is DMA'd in place; after mscan_host_fence it may
+    be overwritten and submitted again (the double-buffering contract of the staging path)."""
+    p = kats.env_params()
+    a = ms.synth_host(ms.synth_preset(0, 31), 0, 90)
+    b = ms.synth_host(ms.synth_preset(0, 32), 0, 90)
+    n = max(len(a[2]), len(b[2]))
+    buf = np.zeros(n, ms.MV_DTYPE)
+    with ms.Context(0, p, 0, 8 << 20) as ctx:
+        ctx.host_register(buf)
+        ctx.video_open(1, 1920, 1080)
+        ctx.video_open(2, 1920, 1080)
+        buf[: len(a[2])] = a[2]
+        ctx.submit(1, a[3], a[0], buf)
+        ctx.host_fence()                 # every byte of video 1 has left `buf`
+        buf[: len(b[2])] = b[2]          # overwrite while video 1's kernels may still be running
+        ctx.submit(2, b[3], b[0], buf)
+        f1, c1 = ctx.collect(1)
+        f2, c2 = ctx.collect(2)
+        st = ctx.stats()
+        ctx.host_unregister(buf)
+    cfg = cfg_for(p, 1920, 1080)
+    for (cnt, off, recs, pts), f, c in ((a, f1, c1), (b, f2, c2)):
+        of, oc = orc.scan_frames(cfg, recs, off, threads=4)
+        assert np.array_equal(c, oc) and np.array_equal(f, of)
+    assert f1.any() and f2.any() and not np.array_equal(c1, c2)
+    assert st.h2d_bytes >= 40 * (len(a[2]) + len(b[2]))
