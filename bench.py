@@ -401,25 +401,71 @@ def run_gpu(args):
     del pin, dev
     pcie_gbs = allmax(pcie_gbs)
 
+    # ---- K-A on projected records, device-resident (what the host-fed default launches) ----------------
+    packed = None
+    if not args.no_packed:
+        d_r8 = ctx.dev_alloc(8 * n_rec + 256)
+        ctx.pack_records_device(d_recs, n_rec, d_r8, sh)
+        stream.synchronize()
+        d_flags8 = ctx.dev_alloc(n_frames)
+        d_counts8 = ctx.dev_alloc(4 * n_frames)
+        for _ in range(3):
+            ctx.scan_device_packed(d_r8, d_off, None, [geom], n_frames, d_flags8, d_counts8, sh)
+        stream.synchronize()
+        ctx.reset_stats()
+        ctx.set_profiling(True)
+        for _ in range(args.steps):
+            ctx.scan_device_packed(d_r8, d_off, None, [geom], n_frames, d_flags8, d_counts8, sh)
+        stream.synchronize()
+        pst = ctx.stats()
+        ctx.set_profiling(False)
+        pk_ms = allmax(pst.scan_ms / max(pst.scan_launches, 1))
+        flags8 = np.zeros(n_frames, np.uint8)
+        ctx.d2h(flags8, d_flags8)
+        packed = {
+            "kernel": "ka_scan_kernel<packed>",
+            "ms_per_launch": pk_ms,
+            "records_per_s": allsum(float(n_rec)) / (pk_ms * 1e-3),
+            "bytes_per_record": 8,
+            "achieved_gbs": (8 * n_rec + FRAME_BYTES * n_frames) / (pk_ms * 1e-3) / 1e9,
+            "matches_native": bool(np.array_equal(flags8, flags)),
+        }
+        for d in (d_r8, d_flags8, d_counts8):
+            ctx.dev_free(d)
+
     # ---- e2e: host-fed through the C ABI ------------------------------------------------------------
-    # host-resident sample: the leading frames of the stream, bounded by --e2e-records (~3.6 GB pinned)
+    # host-resident sample: the leading frames of the stream, bounded by --e2e-records (~3.6 GB pinned).
+    # Three ways for host records to reach the GPU (include/motionscan.h):
+    #   native_inplace  native 40-B records DMA'd straight out of the caller's pinned buffer (no host pass)
+    #   projected       the library's staging pass keeps bytes 6..13 of each record (pool of host threads)
+    #                   and DMAs 8 B/record — what mscan_submit does by default for pageable memory
+    #   packed_pinned   the caller hands over records it projected itself (mscan_pack_records on the
+    #                   decoder's cache-hot side data); only the DMA + kernels are inside the timed region
+    # `e2e.value` is the best of the two modes that start from native host records.
     e2e_frames = int(min(max(np.searchsorted(off, np.uint64(int(args.e2e_records)), side="right") - 1, 1), n_frames))
     if args.e2e_frames:
         e2e_frames = min(args.e2e_frames, n_frames)
     e_rec = int(off[e2e_frames])
     h_recs = ctx.pinned_array(e_rec, ms.MV_DTYPE)
+    h_r8 = ctx.pinned_array(e_rec, ms.MV8_DTYPE)
     h_pts = ctx.pinned_array(e2e_frames, np.float64)
     h_cnt = np.diff(off[: e2e_frames + 1]).astype(np.uint32)
     ctx.d2h(h_recs, d_recs)
     ctx.d2h(h_pts, d_pts)
+    ms.pack_records(h_recs, h_r8)
     e_voff = list(range(0, e2e_frames, fpv)) + [e2e_frames]
+    pack_threads = max(1, len(os.sched_getaffinity(0)) // world)  # ranks share the box's cores
+    ctx.set_pack_threads(pack_threads)
 
-    def e2e_step():
+    def e2e_step(mode):
         vids = []
         for v in range(len(e_voff) - 1):
             a, b = e_voff[v], e_voff[v + 1]
             ctx.video_open(v, spec.width, spec.height)
-            ctx.submit_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_recs.ctypes.data + REC_BYTES * int(off[a]))
+            if mode == "packed_pinned":
+                ctx.submit_packed_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_r8.ctypes.data + 8 * int(off[a]))
+            else:
+                ctx.submit_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_recs.ctypes.data + REC_BYTES * int(off[a]))
             vids.append(v)
         out = [ctx.collect(v) for v in vids]
         segs = ctx.segments_batch(vids, [(e_voff[v + 1] - e_voff[v]) / spec.fps for v in vids])
@@ -428,22 +474,37 @@ def run_gpu(args):
         return out, segs
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        e2e_out = e2e_step()
-    ctx.sync()
-    ctx.reset_stats()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_out = e2e_step()
-    ctx.sync()
-    e2e_dt = allmax(time.perf_counter() - t0)
-    est = ctx.stats()
-    e2e_value = allsum(float(e_rec)) * e2e_steps / e2e_dt
-    e2e_launches = int(est.scan_launches + est.segment_launches)
-    # the host-fed results must equal the device-resident ones for the same frames
-    e_flags = np.concatenate([o[0] for o in e2e_out[0]])
-    e2e_ok = bool(np.array_equal(e_flags, flags[:e2e_frames]))
+    modes = {}
+    for mode in ("native_inplace", "projected", "packed_pinned"):
+        ctx.set_staging_mode(ms.STAGING_PACK if mode == "projected" else ms.STAGING_AUTO)
+        for _ in range(2):
+            e2e_out = e2e_step(mode)
+        ctx.sync()
+        ctx.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_out = e2e_step(mode)
+        ctx.sync()
+        dt = allmax(time.perf_counter() - t0)
+        est = ctx.stats()
+        e_flags = np.concatenate([o[0] for o in e2e_out[0]])
+        modes[mode] = {
+            "value": allsum(float(e_rec)) * e2e_steps / dt,
+            "h2d_bytes_per_step": int(est.h2d_bytes // e2e_steps),
+            "d2h_bytes_per_step": int(est.d2h_bytes // e2e_steps),
+            "h2d_gbs": est.h2d_bytes / dt / 1e9,
+            "launches": int(est.scan_launches + est.segment_launches),
+            # the host-fed results must equal the device-resident ones for the same frames
+            "matches_device_resident": bool(np.array_equal(e_flags, flags[:e2e_frames])),
+        }
+        if mode == "projected":
+            modes[mode]["host_threads"] = pack_threads
+            modes[mode]["project_ms_per_step"] = est.project_ms / e2e_steps
+    ctx.set_staging_mode(ms.STAGING_AUTO)
+    e2e_mode = max(("native_inplace", "projected"), key=lambda m: modes[m]["value"])
+    best = modes[e2e_mode]
+    e2e_value, e2e_launches, e2e_ok = best["value"], best["launches"], all(m["matches_device_resident"] for m in modes.values())
 
     # ---- CPU baseline on rank 0, N=1 only ------------------------------------------------------------
     cpu = None
@@ -501,19 +562,25 @@ def run_gpu(args):
             "e2e": {
                 "value": e2e_value,
                 "unit": UNIT,
-                "h2d_bytes_per_step": int(est.h2d_bytes // e2e_steps),
-                "d2h_bytes_per_step": int(est.d2h_bytes // e2e_steps),
+                "h2d_bytes_per_step": best["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": best["d2h_bytes_per_step"],
+                "mode": e2e_mode,
                 "steps": e2e_steps,
                 "frames": e2e_frames,
                 "records": e_rec,
-                "h2d_gbs": est.h2d_bytes / e2e_dt / 1e9,
+                "h2d_gbs": best["h2d_gbs"],
                 "pcie_peak_gbs": pcie_gbs,
-                "pcie_frac": (est.h2d_bytes / e2e_dt / 1e9) / pcie_gbs if pcie_gbs > 0 else None,
+                "pcie_frac": best["h2d_gbs"] / pcie_gbs if pcie_gbs > 0 else None,
                 "pcie_peak_how": "pinned cudaMemcpyAsync H2D, 1 GiB, best of 9, CUDA events (per GPU)",
                 "launches": e2e_launches,
                 "matches_device_resident": e2e_ok,
-                "how": "mscan_video_open/submit (pinned host records DMA'd in place)/collect/segments_batch/close per step",
+                "modes": modes,
+                "how": "per step: mscan_video_open / mscan_submit of native 40-B host records / collect / segments_batch / close; "
+                "value = best of native_inplace (pinned records DMA'd in place, 40 B/record over PCIe) and projected (the "
+                "library's staging pass keeps the 8 bytes the path reads, 8 B/record over PCIe); packed_pinned (caller-projected "
+                "records) is reported in modes only",
             },
+            "packed_kernel": packed,
             "cpu_baseline": cpu,
             "clocks": sampler.summary(),
             "gpu_launches": launches,
@@ -528,6 +595,7 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     ctx.host_free(h_recs.ctypes.data)
+    ctx.host_free(h_r8.ctypes.data)
     ctx.host_free(h_pts.ctypes.data)
     ctx.close()
     D.close()
@@ -549,6 +617,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=0, help="override: frames of the CPU sample")
     ap.add_argument("--slab-mb", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-packed", action="store_true", help="skip the device-resident K-A<packed> measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -14,6 +14,9 @@
  *   mscan_video_open        <- grid/margin derivation src/motion_scanner.cpp:189-199
  *   mscan_submit            <- the per-frame call `check_frame(frame)` src/motion_scanner.cpp:376
  *                              (decl include/motion_trim/motion_scanner.hpp:106), batched
+ *   mscan_submit_packed / mscan_pack_records / mscan_mv8
+ *                           <- same call site; the record is the byte range [6,14) of AVMotionVector,
+ *                              i.e. exactly the fields read at src/motion_scanner.cpp:243-256
  *   mscan_collect           <- `if (has_motion) ts.push_back(pts)` src/motion_scanner.cpp:382-383
  *   mscan_segments[_batch]  <- merge/segment/decision block src/pipeline.cpp:297-404
  *                              (sort+unique :302-304, no-motion :308-319, builder :325-344,
@@ -36,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MSCAN_ABI_VERSION 1
+#define MSCAN_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 enum {
@@ -68,6 +71,24 @@ typedef struct mscan_mv {
   uint16_t motion_scale; /* @32 */
   /* 6 bytes padding → sizeof == 40 */
 } mscan_mv;
+
+/* ---- projected record: the 8 bytes of AVMotionVector the path reads ----- */
+/* Bytes 6..13 of the native record, in place order (src/motion_scanner.cpp:243-256 reads nothing else).
+ * A pure byte projection — no arithmetic of the path moves to the host. Host-fed callers that can afford
+ * one pass over the side data while it is still cache-hot (right after avcodec_receive_frame) send
+ * 8 B/record over PCIe instead of 40. */
+typedef struct mscan_mv8 {
+  int16_t src_x, src_y;
+  int16_t dst_x, dst_y;
+} mscan_mv8;
+
+/* ---- how mscan_submit moves native records to the GPU -------------------- */
+enum {
+  MSCAN_STAGING_AUTO = 0,  /* pinned source: DMA the native records in place (no host pass);
+                              pageable source: the staging pass projects to mscan_mv8 (default)  */
+  MSCAN_STAGING_PACK = 1,  /* always project on the host, even from pinned memory                */
+  MSCAN_STAGING_NATIVE = 2 /* never project: pageable sources are memcpy'd as 40-byte records    */
+};
 
 /* ---- TimeSegment (include/motion_trim/types.hpp:56-59) ----------------- */
 typedef struct mscan_segment {
@@ -120,6 +141,8 @@ typedef struct mscan_stats {
   uint64_t d2h_bytes;
   double scan_ms;            /* Σ K-A durations, only while profiling is enabled         */
   double segment_ms;         /* Σ K-C durations, only while profiling is enabled         */
+  uint64_t records_projected; /* native records the staging pass projected to mscan_mv8  */
+  double project_ms;          /* host wall time spent in that projection                 */
 } mscan_stats;
 
 typedef struct mscan_ctx mscan_ctx;
@@ -158,11 +181,26 @@ int mscan_video_open_geometry(mscan_ctx* ctx, uint32_t video_id, const mscan_geo
  * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / mscan_host_register /
  * cudaHostRegister) it is DMA'd in place and must stay valid until the copy has completed, i.e. until
  * mscan_host_fence, mscan_sync, mscan_collect* or mscan_segments* returns (mscan_flush only enqueues);
- * pageable memory is copied into the library's pinned ring before the call returns.
+ * pageable memory is consumed before the call returns: its records are projected to mscan_mv8 (the 8
+ * bytes the path reads) straight into the library's pinned ring — see mscan_set_staging_mode.
  * first_frame_out (may be NULL): index, in the video's submission order, of this call's first
  * frame — what a chunk worker needs to read back its own frames with mscan_collect_range. */
 int mscan_submit(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
                  const uint32_t* rec_count, const mscan_mv* recs, uint64_t* first_frame_out);
+/* Same, for records the caller has already projected (mscan_pack_records, or a decoder front-end that
+ * writes mscan_mv8 directly). recs must be 8-byte aligned. Pinned memory is DMA'd in place (same
+ * lifetime rule as above), pageable memory is copied into the pinned ring. Native and packed submits
+ * may be mixed freely, also within one video: a slab (= one K-A launch) holds one format. */
+int mscan_submit_packed(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
+                        const uint32_t* rec_count, const mscan_mv8* recs, uint64_t* first_frame_out);
+/* The projection itself, usable from any thread without a context or a GPU: out[i] = bytes 6..13 of
+ * recs[i]. out must be 8-byte aligned; written with streaming stores (it is read next by the DMA engine). */
+int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out);
+/* MSCAN_STAGING_*; default AUTO. */
+int mscan_set_staging_mode(mscan_ctx* ctx, int mode);
+/* Threads (including the caller) that project one large submit; 0 → as many as the process may run on
+ * (sched_getaffinity), or $MSCAN_PACK_THREADS. Submits below 256 Ki records never leave the calling thread. */
+int mscan_set_pack_threads(mscan_ctx* ctx, int n_threads);
 int mscan_flush(mscan_ctx* ctx); /* launch whatever is staged; does not wait */
 /* Per-frame results in submission order. cap = capacity of flags/full_counts (either may be NULL). */
 int mscan_collect(mscan_ctx* ctx, uint32_t video_id, uint8_t* flags, uint32_t* full_counts,
@@ -210,6 +248,13 @@ int mscan_offsets_from_counts(mscan_ctx* ctx, const uint32_t* d_rec_count, uint3
 int mscan_scan_device(mscan_ctx* ctx, const mscan_mv* d_recs, const uint64_t* d_rec_off,
                       const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms,
                       uint32_t n_frames, uint8_t* d_flags, uint32_t* d_full_counts, void* stream);
+/* Same on projected records (16-byte aligned base; frames may start at any record; the buffer must be
+ * readable for 16 bytes past its last record). */
+int mscan_scan_device_packed(mscan_ctx* ctx, const mscan_mv8* d_recs, const uint64_t* d_rec_off,
+                             const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms,
+                             uint32_t n_frames, uint8_t* d_flags, uint32_t* d_full_counts, void* stream);
+/* mscan_pack_records for records already in device memory (8-byte aligned buffers). */
+int mscan_pack_records_device(mscan_ctx* ctx, const mscan_mv* d_recs, uint64_t n, mscan_mv8* d_out, void* stream);
 /* K-C on device memory: video v owns frames [h_video_off[v], h_video_off[v+1]) of d_pts/d_flags.
  * d_segments: capacity = h_video_off[n_videos] entries; video v's segments start at
  * d_segments[h_video_off[v]]. d_results[n_videos]. Asynchronous on `stream`. */

@@ -30,7 +30,7 @@ namespace mscan {
 
 namespace {
 
-constexpr int kTileRec = 512;                      // records per ring stage
+constexpr int kTileRec = 512;                      // native records per ring stage
 constexpr int kTileBytes = kTileRec * kRecBytes;   // 20480, multiple of lcm(16,40)=80
 // consumer warps per CTA: 8 when two CTAs share an SM, 16 when only one fits (4K grids: the sweep in
 // tools/ka_sweep.py shows one CTA of 8 consumer warps cannot keep up with HBM)
@@ -72,9 +72,14 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
 // half reaches 0x7FFF, and since at most kCons lanes × 32 merged votes can pass the guard concurrently
 // a half never carries into its neighbour. Counts >= 0x7FFF are reported as "many": exact for the
 // active test because VECTORS_NEEDED <= 255.
-template <bool kGlobalCnt, int kConsWarps, bool kCnt16>
+// kPacked: the slab holds 8-byte projections of the records (bytes 6..13 of AVMotionVector: src_x, src_y,
+// dst_x, dst_y — mscan_mv8) instead of the native 40-byte layout. Same ring, same stage size; a stage then
+// carries 2560 records, and since an 8-byte record never straddles a 16-byte boundary the tiles are cut
+// on the aligned byte stream rather than on record counts.
+template <bool kGlobalCnt, int kConsWarps, bool kCnt16, bool kPacked>
 __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
   static_assert(!(kGlobalCnt && kCnt16), "global counters are always 32-bit");
+  constexpr uint32_t kStride = kPacked ? kPackedBytes : kRecBytes;
   constexpr int kCons = kConsWarps * 32;
   constexpr int kThreads = kCons + 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -121,19 +126,32 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           a.counts[f_cur] = 0;
         } else {
           const uint32_t n = (uint32_t)n64;
-          const uint64_t byte0 = m_cur.o0 * (uint64_t)kRecBytes;
+          const uint64_t byte0 = m_cur.o0 * (uint64_t)kStride;
           const uint32_t d = (uint32_t)(byte0 & 15u);
           const unsigned char* src = a.recs + (byte0 - d);
-          const uint32_t n_tiles = (n + kTileRec - 1) / kTileRec;
+          // native: tile t holds records [512t, 512t+512); packed: tile t holds the records that lie in
+          // bytes [20480t, 20480t+20480) of the 16-byte aligned stream starting at src
+          const uint32_t n_tiles = kPacked ? (uint32_t)((d + (uint64_t)kPackedBytes * n + kTileBytes - 1) / kTileBytes)
+                                           : (n + kTileRec - 1) / kTileRec;
           for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t nr = min((uint32_t)kTileRec, n - t * kTileRec);
-            // full tiles copy kTileBytes; the last one stops at the end of the last record's
-            // 16 useful bytes, rounded up to 16 (never past the record's own 40 bytes)
-            const uint32_t bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((d + kRecBytes * (nr - 1) + 16u + 15u) & ~15u);
+            uint32_t nr, bytes, boff;
+            if (kPacked) {
+              const uint32_t r_lo = t ? (uint32_t)(((uint64_t)t * kTileBytes - d) / kPackedBytes) : 0u;
+              const uint32_t r_hi = (uint32_t)min((uint64_t)n, ((uint64_t)(t + 1) * kTileBytes - d) / kPackedBytes);
+              nr = r_hi - r_lo;
+              boff = t ? 0u : d;
+              bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((boff + kPackedBytes * nr + 15u) & ~15u);
+            } else {
+              nr = min((uint32_t)kTileRec, n - t * kTileRec);
+              boff = d;
+              // full tiles copy kTileBytes; the last one stops at the end of the last record's
+              // 16 useful bytes, rounded up to 16 (never past the record's own 40 bytes)
+              bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((d + kRecBytes * (nr - 1) + 16u + 15u) & ~15u);
+            }
             mbar_wait(bar_empty0 + 8 * stage, phase ^ 1u);
             TileDesc td;
             td.n_rec = nr;
-            td.byte_off = d;
+            td.byte_off = boff;
             td.frame = f_cur;
             td.last = (t + 1 == n_tiles) ? 1u : 0u;
             td.gw = m_cur.g.gw;
@@ -181,13 +199,22 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
         const uint32_t r = r0 + lane;
         int32_t key = -1;
         if (r < td.n_rec) {
-          const unsigned char* p = base + (size_t)r * kRecBytes;
-          const uint32_t w1 = *reinterpret_cast<const uint32_t*>(p + 4);  // w | h<<8 | src_x<<16
-          const uint2 w23 = *reinterpret_cast<const uint2*>(p + 8);       // src_y | dst_x<<16, dst_y | pad<<16
-          const int32_t sx = (int32_t)w1 >> 16;
-          const int32_t sy = (int32_t)(int16_t)(w23.x & 0xFFFFu);
-          const int32_t tx = (int32_t)w23.x >> 16;
-          const int32_t ty = (int32_t)(int16_t)(w23.y & 0xFFFFu);
+          int32_t sx, sy, tx, ty;
+          if (kPacked) {
+            const uint2 w = *reinterpret_cast<const uint2*>(base + (size_t)r * kPackedBytes);  // src_x | src_y<<16, dst_x | dst_y<<16
+            sx = (int32_t)(int16_t)(w.x & 0xFFFFu);
+            sy = (int32_t)w.x >> 16;
+            tx = (int32_t)(int16_t)(w.y & 0xFFFFu);
+            ty = (int32_t)w.y >> 16;
+          } else {
+            const unsigned char* p = base + (size_t)r * kRecBytes;
+            const uint32_t w1 = *reinterpret_cast<const uint32_t*>(p + 4);  // w | h<<8 | src_x<<16
+            const uint2 w23 = *reinterpret_cast<const uint2*>(p + 8);       // src_y | dst_x<<16, dst_y | pad<<16
+            sx = (int32_t)w1 >> 16;
+            sy = (int32_t)(int16_t)(w23.x & 0xFFFFu);
+            tx = (int32_t)w23.x >> 16;
+            ty = (int32_t)(int16_t)(w23.y & 0xFFFFu);
+          }
           const int32_t dx = tx - sx, dy = ty - sy;                        // :246-247
           const int32_t mag = (int32_t)((uint32_t)dx * (uint32_t)dx + (uint32_t)dy * (uint32_t)dy);  // :248
           const int32_t gx = tx >> shift, gy = ty >> shift;                // :255-256
@@ -366,15 +393,39 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
   return false;
 }
 
-cudaError_t scan_configure(uint32_t smem_optin) {
-  const int v = (int)smem_optin;
+namespace {
+template <bool kPacked>
+cudaError_t configure_all(int v) {
   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-  cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, false>, attr, v);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, false>, attr, v);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, true>, attr, v);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, true>, attr, v);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 8, false>, attr, v);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 16, false>, attr, v);
+  cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, false, kPacked>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, false, kPacked>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, true, kPacked>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<false, 16, true, kPacked>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 8, false, kPacked>, attr, v);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_kernel<true, 16, false, kPacked>, attr, v);
+  return e;
+}
+
+template <bool kPacked>
+void launch_one(const ScanArgs& a, const ScanPlan& plan, uint32_t grid, cudaStream_t st) {
+  const bool wide = plan.cons_warps == 16;
+  const uint32_t threads = plan.cons_warps * 32 + 32;
+  if (plan.global_cnt) {
+    if (wide) ka_scan_kernel<true, 16, false, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<true, 8, false, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+  } else if (plan.cnt16) {
+    if (wide) ka_scan_kernel<false, 16, true, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<false, 8, true, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+  } else {
+    if (wide) ka_scan_kernel<false, 16, false, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+    else ka_scan_kernel<false, 8, false, kPacked><<<grid, threads, plan.smem_bytes, st>>>(a);
+  }
+}
+}  // namespace
+
+cudaError_t scan_configure(uint32_t smem_optin) {
+  cudaError_t e = configure_all<false>((int)smem_optin);
+  if (e == cudaSuccess) e = configure_all<true>((int)smem_optin);
   return e;
 }
 
@@ -386,18 +437,8 @@ uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames) {
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
   const uint32_t grid = scan_grid(plan, num_sms, a.n_frames);
-  const bool wide = plan.cons_warps == 16;
-  const uint32_t threads = plan.cons_warps * 32 + 32;
-  if (plan.global_cnt) {
-    if (wide) ka_scan_kernel<true, 16, false><<<grid, threads, plan.smem_bytes, st>>>(a);
-    else ka_scan_kernel<true, 8, false><<<grid, threads, plan.smem_bytes, st>>>(a);
-  } else if (plan.cnt16) {
-    if (wide) ka_scan_kernel<false, 16, true><<<grid, threads, plan.smem_bytes, st>>>(a);
-    else ka_scan_kernel<false, 8, true><<<grid, threads, plan.smem_bytes, st>>>(a);
-  } else {
-    if (wide) ka_scan_kernel<false, 16, false><<<grid, threads, plan.smem_bytes, st>>>(a);
-    else ka_scan_kernel<false, 8, false><<<grid, threads, plan.smem_bytes, st>>>(a);
-  }
+  if (a.packed) launch_one<true>(a, plan, grid, st);
+  else launch_one<false>(a, plan, grid, st);
   return cudaGetLastError();
 }
 

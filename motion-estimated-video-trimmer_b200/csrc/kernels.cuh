@@ -9,7 +9,8 @@
 
 namespace mscan {
 
-constexpr int kRecBytes = 40;  // sizeof(AVMotionVector), src/motion_scanner.cpp:226
+constexpr int kRecBytes = 40;    // sizeof(AVMotionVector), src/motion_scanner.cpp:226
+constexpr int kPackedBytes = 8;  // sizeof(mscan_mv8): bytes 6..13 of the native record
 
 // Geometry as the kernel consumes it: rows [y_min, y_max) are live (clamped to the grid).
 struct DevGeom {
@@ -18,7 +19,7 @@ struct DevGeom {
 
 // ---- K-A: vote scatter + cluster count + activity flag (check_frame, motion_scanner.cpp:217-295)
 struct ScanArgs {
-  const uint8_t* recs;         // 16-byte aligned base of 40-byte records
+  const uint8_t* recs;         // 16-byte aligned base of 40-byte records (8-byte when `packed`)
   const uint64_t* rec_off;     // [n_frames+1] record indices
   const uint32_t* frame_geom;  // [n_frames] index into geoms, or nullptr → 0
   const DevGeom* geoms;        // device table
@@ -35,6 +36,7 @@ struct ScanArgs {
   uint32_t max_cells;          // vote counters per CTA (shared memory, or a slice of cnt_scratch)
   uint32_t max_bit_words;      // words per bit-row buffer
   uint32_t adj8;               // extension: 8-neighbour clusters (reference is 4-neighbour only)
+  uint32_t packed;             // records are mscan_mv8 projections, not native AVMotionVector
   uint32_t* cnt_scratch;       // zeroed global scratch, grid × max_cells, only when plan.global_cnt
 };
 
@@ -83,6 +85,7 @@ cudaError_t segments_launch(const SegArgs& a, uint32_t n_videos, cudaStream_t st
 cudaError_t offsets_launch(const uint32_t* counts, uint32_t n, uint64_t* off, uint64_t* block_scratch,
                            cudaStream_t st);
 uint32_t offsets_scratch_elems(uint32_t n);
+cudaError_t project_launch(const mscan_mv* recs, uint64_t n, mscan_mv8* out, cudaStream_t st);
 cudaError_t synth_counts_launch(const mvgen_spec& spec, uint64_t frame0, uint32_t n_frames, uint32_t* counts,
                                 cudaStream_t st);
 cudaError_t synth_fill_launch(const mvgen_spec& spec, uint64_t frame0, uint32_t n_frames, const uint64_t* rec_off,

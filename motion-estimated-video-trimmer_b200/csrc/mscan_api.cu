@@ -8,18 +8,30 @@
 //                   while slab k is being DMA'd and scanned, submit() fills slab k+1
 //                   (memory_io.cpp role: the reference mmaps the file for FFmpeg; here the staged
 //                   thing is the decoder's MV side data on its way to HBM);
+//   * projection  — native records in pageable memory are not memcpy'd into staging: only bytes 6..13
+//                   of each 40-byte record (the four int16 the path reads) are written there, by a
+//                   small worker pool for large submits, so 8 B/record cross PCIe instead of 40;
 //   * K-A per slab, K-C per segments call.
 // There is no CPU implementation of the path behind this ABI.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -57,6 +69,7 @@ struct Slab {
   cudaEvent_t done = nullptr;
   cudaEvent_t copied = nullptr;  // recorded after the slab's last H2D copy (mscan_host_fence)
   bool in_flight = false;
+  bool packed = false;  // the slab holds mscan_mv8 projections (8 B) instead of native records (40 B)
   uint64_t bytes = 0;
   uint64_t recs = 0;
   uint32_t frames = 0;
@@ -67,6 +80,130 @@ struct EvPair {
   cudaEvent_t a, b;
   int kind;  // 0 = K-A, 1 = K-C
 };
+
+// ---- host projection AVMotionVector → mscan_mv8 -------------------------------------------------
+// Bytes 6..13 of a native record are src_x, src_y, dst_x, dst_y (motion_scanner.cpp:243-256 reads
+// nothing else), contiguous: the projection is one unaligned 8-byte load and one store per record.
+// Streaming stores: the staging buffer is read next by the DMA engine, not by this core.
+void project_records(const uint8_t* in, uint64_t n, uint64_t* out) {
+  for (uint64_t i = 0; i < n; ++i) {
+#if defined(__x86_64__)
+    // 8 records = 5 cache lines; software prefetch 4 KB ahead measured +13 % from DRAM on the B200 box's
+    // host (tools/exp_hostfeed.cu), free when the source is cache-hot. Prefetches never fault.
+    if ((i & 7u) == 0) {
+      const char* q = reinterpret_cast<const char*>(in + (size_t)kRecBytes * i + 4096);
+      _mm_prefetch(q, _MM_HINT_T0);
+      _mm_prefetch(q + 64, _MM_HINT_T0);
+      _mm_prefetch(q + 128, _MM_HINT_T0);
+      _mm_prefetch(q + 192, _MM_HINT_T0);
+      _mm_prefetch(q + 256, _MM_HINT_T0);
+    }
+#endif
+    uint64_t v;
+    std::memcpy(&v, in + (size_t)kRecBytes * i + 6, sizeof v);
+#if defined(__x86_64__)
+    _mm_stream_si64(reinterpret_cast<long long*>(out + i), (long long)v);
+#else
+    out[i] = v;
+#endif
+  }
+#if defined(__x86_64__)
+  _mm_sfence();
+#endif
+}
+
+constexpr uint64_t kPoolChunk = 32768;      // records per work item (1.3 MB of native records)
+constexpr uint64_t kPoolMinRecs = 1 << 18;  // smaller jobs are projected by the calling thread alone
+
+// Parallel-for over one projection job; the calling thread takes part. One job at a time (callers
+// hold the context mutex).
+class PackPool {
+ public:
+  explicit PackPool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this] { worker(); });
+  }
+  ~PackPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int workers() const { return (int)th_.size(); }
+
+  void run(const uint8_t* src, uint64_t* dst, uint64_t n) {
+    const uint64_t total = (n + kPoolChunk - 1) / kPoolChunk;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      idle_cv_.wait(lk, [this] { return active_ == 0; });  // stragglers of the previous job have left
+      src_ = src;
+      dst_ = dst;
+      n_ = n;
+      total_ = total;
+      next_.store(0, std::memory_order_relaxed);
+      done_.store(0, std::memory_order_relaxed);
+      ++gen_;
+    }
+    cv_.notify_all();
+    drain(src, dst, n, total);
+    std::unique_lock<std::mutex> lk(mu_);
+    idle_cv_.wait(lk, [&] { return done_.load(std::memory_order_acquire) == total && active_ == 0; });
+  }
+
+ private:
+  void drain(const uint8_t* src, uint64_t* dst, uint64_t n, uint64_t total) {
+    for (uint64_t k = next_.fetch_add(1, std::memory_order_relaxed); k < total; k = next_.fetch_add(1, std::memory_order_relaxed)) {
+      const uint64_t a = k * kPoolChunk, b = std::min(n, a + kPoolChunk);
+      project_records(src + (size_t)kRecBytes * a, b - a, dst + a);
+      done_.fetch_add(1, std::memory_order_release);
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      const uint8_t* src;
+      uint64_t *dst, n, total;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        src = src_;
+        dst = dst_;
+        n = n_;
+        total = total_;
+        ++active_;  // joined under the lock: run() will not post the next job until we have left
+      }
+      drain(src, dst, n, total);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        --active_;
+      }
+      idle_cv_.notify_all();
+    }
+  }
+
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, idle_cv_;
+  bool stop_ = false;
+  uint64_t gen_ = 0;
+  int active_ = 0;
+  const uint8_t* src_ = nullptr;
+  uint64_t* dst_ = nullptr;
+  uint64_t n_ = 0, total_ = 0;
+  std::atomic<uint64_t> next_{0}, done_{0};
+};
+
+int default_pack_threads() {
+  if (const char* e = std::getenv("MSCAN_PACK_THREADS")) return std::max(1, std::atoi(e));
+  cpu_set_t set;
+  int n = 0;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);  // honours taskset / cgroup cpusets
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(n, 64));
+}
 
 }  // namespace
 
@@ -126,6 +263,11 @@ struct mscan_ctx {
   std::vector<DevGeom> user_geoms_cached;  // what d_user_geoms currently holds
   // last job table uploaded by mscan_segments_device (re-used when unchanged: no sync, no copy)
   std::vector<SegJob> dev_jobs_cached;
+
+  // host projection (see project_records)
+  int staging_mode = MSCAN_STAGING_AUTO;
+  int pack_threads = 0;  // 0 → default_pack_threads() at first use
+  std::unique_ptr<PackPool> pool;
 
   mscan_stats stats{};
   bool profiling = false;
@@ -281,6 +423,7 @@ int launch_slab(mscan_ctx* c, Slab& s) {
   CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of this slab precedes this point
   ScanArgs a = base_args(c);
   a.recs = s.d_recs;
+  a.packed = s.packed ? 1u : 0u;
   a.rec_off = s.d_rec_off;
   a.frame_geom = s.d_geom;
   a.geoms = c->d_geoms;
@@ -695,8 +838,9 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
   return mscan_video_open_geometry(c, video_id, &g);
 }
 
-int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                 const mscan_mv* recs, uint64_t* first_frame_out) {
+// Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
+static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                       const void* recs, bool src_packed, uint64_t* first_frame_out) {
   if (!c) return MSCAN_ERR_INVALID;
   if (n_frames == 0) {
     if (first_frame_out) {
@@ -725,16 +869,36 @@ int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const doubl
   }
   const uint8_t* src = reinterpret_cast<const uint8_t*>(recs);
   const bool pinned = recs && is_pinned(recs);
+  // How the records reach the slab: native+pinned → DMA in place (40 B/record over PCIe, no host work);
+  // native+pageable → the staging pass writes only the 8 bytes the path reads (8 B/record over PCIe);
+  // packed → as is (DMA in place when pinned, memcpy into staging otherwise).
+  bool project = false;
+  if (!src_packed) {
+    if (c->staging_mode == MSCAN_STAGING_PACK) project = true;
+    else if (c->staging_mode == MSCAN_STAGING_NATIVE) project = false;
+    else project = !pinned;
+  }
+  const bool slab_packed = src_packed || project;
+  const uint64_t in_stride = src_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
+  const uint64_t out_stride = slab_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
+  // projected sub-batches are DMA'd as they are produced, so the copy of one overlaps the projection of the next
+  const uint64_t max_take_recs = project ? (4ull << 20) : ~0ull;
   uint32_t f = 0;
   uint64_t src_rec = 0;
   while (f < n_frames) {
     Slab* s = &c->slabs[c->cur];
+    if (s->frames && s->packed != slab_packed) {  // one record format per slab (one K-A launch)
+      int rc = flush_locked(c);
+      if (rc) return rc;
+      continue;
+    }
     // how many whole frames fit into the current slab
     uint32_t take = 0;
     uint64_t take_recs = 0;
     while (f + take < n_frames && s->frames + take < c->slab_frames) {
-      const uint64_t nb = (take_recs + rec_count[f + take]) * (uint64_t)kRecBytes;
+      const uint64_t nb = (take_recs + rec_count[f + take]) * out_stride;
       if (s->bytes + nb > c->slab_bytes) break;
+      if (take && take_recs + rec_count[f + take] > max_take_recs) break;
       take_recs += rec_count[f + take];
       ++take;
     }
@@ -747,16 +911,36 @@ int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const doubl
       if (rc) return rc;
       continue;
     }
-    if (s->frames == 0) s->log_base = c->log_head;
-    const uint64_t nbytes = take_recs * (uint64_t)kRecBytes;
+    if (s->frames == 0) {
+      s->log_base = c->log_head;
+      s->packed = slab_packed;
+    }
+    const uint64_t nbytes = take_recs * out_stride;
     if (nbytes) {
       if (!recs) return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
-      const uint8_t* from = src + src_rec * (uint64_t)kRecBytes;
-      if (pinned) {
+      const uint8_t* from = src + src_rec * in_stride;
+      if (!project && pinned) {
         CU(cudaMemcpyAsync(s->d_recs + s->bytes, from, nbytes, cudaMemcpyHostToDevice, s->stream));
       } else {
         if (!s->h_recs) CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
-        std::memcpy(s->h_recs + s->bytes, from, nbytes);
+        if (project) {
+          const auto t0 = std::chrono::steady_clock::now();
+          uint64_t* to = reinterpret_cast<uint64_t*>(s->h_recs + s->bytes);
+          if (take_recs >= kPoolMinRecs) {
+            if (!c->pool) {
+              const int nthr = c->pack_threads > 0 ? c->pack_threads : default_pack_threads();
+              c->pool.reset(new PackPool(nthr - 1));
+            }
+            if (c->pool->workers() > 0) c->pool->run(from, to, take_recs);
+            else project_records(from, take_recs, to);
+          } else {
+            project_records(from, take_recs, to);
+          }
+          c->stats.project_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+          c->stats.records_projected += take_recs;
+        } else {
+          std::memcpy(s->h_recs + s->bytes, from, nbytes);
+        }
         CU(cudaMemcpyAsync(s->d_recs + s->bytes, s->h_recs + s->bytes, nbytes, cudaMemcpyHostToDevice, s->stream));
       }
       c->stats.h2d_bytes += nbytes;
@@ -784,6 +968,41 @@ int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const doubl
       if (rc) return rc;
     }
   }
+  return MSCAN_OK;
+}
+
+int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                 const mscan_mv* recs, uint64_t* first_frame_out) {
+  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, false, first_frame_out);
+}
+
+int mscan_submit_packed(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                        const mscan_mv8* recs, uint64_t* first_frame_out) {
+  if (recs && (reinterpret_cast<uintptr_t>(recs) & 7u)) return fail(c, MSCAN_ERR_INVALID, "packed records must be 8-byte aligned");
+  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, true, first_frame_out);
+}
+
+int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out) {
+  if (n && (!recs || !out)) return MSCAN_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(out) & 7u) return MSCAN_ERR_INVALID;
+  project_records(reinterpret_cast<const uint8_t*>(recs), n, reinterpret_cast<uint64_t*>(out));
+  return MSCAN_OK;
+}
+
+int mscan_set_staging_mode(mscan_ctx* c, int mode) {
+  if (!c) return MSCAN_ERR_INVALID;
+  if (mode != MSCAN_STAGING_AUTO && mode != MSCAN_STAGING_PACK && mode != MSCAN_STAGING_NATIVE)
+    return fail(c, MSCAN_ERR_INVALID, "unknown staging mode %d", mode);
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->staging_mode = mode;
+  return MSCAN_OK;
+}
+
+int mscan_set_pack_threads(mscan_ctx* c, int n_threads) {
+  if (!c || n_threads < 0) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->pack_threads = n_threads;
+  c->pool.reset();  // re-created with the new size at the next large projection
   return MSCAN_OK;
 }
 
@@ -1106,9 +1325,9 @@ int mscan_offsets_from_counts(mscan_ctx* c, const uint32_t* d_cnt, uint32_t n, u
   return MSCAN_OK;
 }
 
-int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_rec_off, const uint32_t* d_frame_geom,
-                      const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames, uint8_t* d_flags,
-                      uint32_t* d_counts, void* stream) {
+static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const uint64_t* d_rec_off,
+                            const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames,
+                            uint8_t* d_flags, uint32_t* d_counts, void* stream) {
   if (!c || !d_rec_off || !geoms || n_geoms == 0 || !d_flags || !d_counts) return MSCAN_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(d_recs) & 15u) != 0) return fail(c, MSCAN_ERR_INVALID, "d_recs must be 16-byte aligned");
   if (n_geoms > kMaxGeoms) return fail(c, MSCAN_ERR_CAPACITY, "too many geometries");
@@ -1144,6 +1363,7 @@ int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_re
   }
   ScanArgs a = base_args(c);
   a.recs = reinterpret_cast<const uint8_t*>(d_recs);
+  a.packed = packed ? 1u : 0u;
   a.rec_off = d_rec_off;
   a.frame_geom = d_frame_geom;
   a.geoms = c->d_user_geoms;
@@ -1154,6 +1374,29 @@ int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_re
   a.max_cells = cells;
   a.max_bit_words = words;
   return run_scan(c, a, plan, st, 0);
+}
+
+int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_rec_off, const uint32_t* d_frame_geom,
+                      const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames, uint8_t* d_flags,
+                      uint32_t* d_counts, void* stream) {
+  return scan_device_impl(c, d_recs, false, d_rec_off, d_frame_geom, geoms, n_geoms, n_frames, d_flags, d_counts, stream);
+}
+
+int mscan_scan_device_packed(mscan_ctx* c, const mscan_mv8* d_recs, const uint64_t* d_rec_off, const uint32_t* d_frame_geom,
+                             const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames, uint8_t* d_flags,
+                             uint32_t* d_counts, void* stream) {
+  return scan_device_impl(c, d_recs, true, d_rec_off, d_frame_geom, geoms, n_geoms, n_frames, d_flags, d_counts, stream);
+}
+
+int mscan_pack_records_device(mscan_ctx* c, const mscan_mv* d_recs, uint64_t n, mscan_mv8* d_out, void* stream) {
+  if (!c || (n && (!d_recs || !d_out))) return MSCAN_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(d_recs) & 7u) || (reinterpret_cast<uintptr_t>(d_out) & 7u))
+    return fail(c, MSCAN_ERR_INVALID, "device record buffers must be 8-byte aligned");
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  CU(project_launch(d_recs, n, d_out, stream ? (cudaStream_t)stream : c->main_stream));
+  c->stats.aux_launches += 1;
+  return MSCAN_OK;
 }
 
 int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_video_off, const double* h_durations,

@@ -158,7 +158,23 @@ __global__ void __launch_bounds__(256) synth_fill_kernel(const __grid_constant__
   }
 }
 
+// Device-side projection AVMotionVector → mscan_mv8 (bytes 6..13). Records are 8-byte aligned, so the
+// range is the top 2 bytes of word 0 and the low 6 bytes of word 1.
+__global__ void __launch_bounds__(256) project_kernel(const uint64_t* __restrict__ recs, uint64_t n,
+                                                       uint64_t* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t w0 = recs[5 * i], w1 = recs[5 * i + 1];
+    out[i] = (w0 >> 48) | (w1 << 16);
+  }
+}
+
 }  // namespace
+
+cudaError_t project_launch(const mscan_mv* recs, uint64_t n, mscan_mv8* out, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  project_kernel<<<148 * 8, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(recs), n, reinterpret_cast<uint64_t*>(out));
+  return cudaGetLastError();
+}
 
 uint32_t offsets_scratch_elems(uint32_t) { return 0; }
 

@@ -26,7 +26,10 @@ MV_DTYPE = np.dtype(
         "itemsize": 40,
     }
 )
+# mscan_mv8: bytes 6..13 of the native record
+MV8_DTYPE = np.dtype([("src_x", "<i2"), ("src_y", "<i2"), ("dst_x", "<i2"), ("dst_y", "<i2")])
 SEG_DTYPE = np.dtype([("start", "<f8"), ("end", "<f8")])
+STAGING_AUTO, STAGING_PACK, STAGING_NATIVE = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -71,6 +74,8 @@ class Stats(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("scan_ms", C.c_double),
         ("segment_ms", C.c_double),
+        ("records_projected", C.c_uint64),
+        ("project_ms", C.c_double),
     ]
 
 
@@ -131,6 +136,10 @@ SYMBOLS = {
     "mscan_video_open": (_i, [_vp, _u32, _i, _i]),
     "mscan_video_open_geometry": (_i, [_vp, _u32, _P(Geometry)]),
     "mscan_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _P(_u64)]),
+    "mscan_submit_packed": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _P(_u64)]),
+    "mscan_pack_records": (_i, [_vp, _u64, _vp]),
+    "mscan_set_staging_mode": (_i, [_vp, _i]),
+    "mscan_set_pack_threads": (_i, [_vp, _i]),
     "mscan_collect_range": (_i, [_vp, _u32, _u64, _u32, _vp, _vp]),
     "mscan_flush": (_i, [_vp]),
     "mscan_collect": (_i, [_vp, _u32, _vp, _vp, _u32, _P(_u32)]),
@@ -149,6 +158,8 @@ SYMBOLS = {
     "mscan_memcpy_d2h": (_i, [_vp, _vp, _vp, C.c_size_t]),
     "mscan_offsets_from_counts": (_i, [_vp, _vp, _u32, _vp, _vp]),
     "mscan_scan_device": (_i, [_vp, _vp, _vp, _vp, _P(Geometry), _u32, _u32, _vp, _vp, _vp]),
+    "mscan_scan_device_packed": (_i, [_vp, _vp, _vp, _vp, _P(Geometry), _u32, _u32, _vp, _vp, _vp]),
+    "mscan_pack_records_device": (_i, [_vp, _vp, _u64, _vp, _vp]),
     "mscan_segments_device": (_i, [_vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mscan_synth_preset": (_i, [_P(MvgenSpec), _i, _u64]),
     "mscan_synth_host_counts": (_i, [_P(MvgenSpec), _u64, _u32, _vp, _i]),
@@ -217,6 +228,18 @@ def geometry_from_dims(p: Params, width: int, height: int) -> Geometry:
     if rc:
         raise MscanError(rc, "mscan_geometry_from_dims")
     return g
+
+
+def pack_records(recs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """mscan_pack_records: the 8-byte projection (MV8_DTYPE) of native records (MV_DTYPE). No GPU needed."""
+    assert recs.dtype == MV_DTYPE and recs.flags["C_CONTIGUOUS"]
+    if out is None:
+        out = np.empty(len(recs), dtype=MV8_DTYPE)
+    assert out.dtype == MV8_DTYPE and len(out) >= len(recs)
+    rc = lib().mscan_pack_records(_ptr(recs), len(recs), _ptr(out))
+    if rc:
+        raise MscanError(rc, "mscan_pack_records")
+    return out
 
 
 def synth_preset(config: int, seed: int) -> MvgenSpec:
@@ -288,6 +311,22 @@ class Context:
 
     def submit_raw(self, vid: int, n_frames: int, pts_ptr: int, cnt_ptr: int, recs_ptr: int):
         self._ck(self.L.mscan_submit(self.h, vid, n_frames, pts_ptr, cnt_ptr, recs_ptr, None))
+
+    def submit_packed(self, vid: int, pts, rec_count, recs8) -> int:
+        """Records already projected to MV8_DTYPE (pack_records)."""
+        n = len(rec_count)
+        first = C.c_uint64()
+        self._ck(self.L.mscan_submit_packed(self.h, vid, n, _ptr(pts), _ptr(rec_count), _ptr(recs8), C.byref(first)))
+        return first.value
+
+    def submit_packed_raw(self, vid: int, n_frames: int, pts_ptr: int, cnt_ptr: int, recs_ptr: int):
+        self._ck(self.L.mscan_submit_packed(self.h, vid, n_frames, pts_ptr, cnt_ptr, recs_ptr, None))
+
+    def set_staging_mode(self, mode: int):
+        self._ck(self.L.mscan_set_staging_mode(self.h, mode))
+
+    def set_pack_threads(self, n: int):
+        self._ck(self.L.mscan_set_pack_threads(self.h, n))
 
     def collect_range(self, vid: int, first: int, n: int):
         flags = np.zeros(n, dtype=np.uint8)
@@ -391,6 +430,17 @@ class Context:
         self._ck(
             self.L.mscan_scan_device(self.h, d_recs, d_off, d_frame_geom, arr, len(geoms), n_frames, d_flags, d_counts, stream)
         )
+
+    def scan_device_packed(self, d_recs8, d_off, d_frame_geom, geoms, n_frames, d_flags, d_counts, stream: int = 0):
+        arr = (Geometry * len(geoms))(*geoms)
+        self._ck(
+            self.L.mscan_scan_device_packed(
+                self.h, d_recs8, d_off, d_frame_geom, arr, len(geoms), n_frames, d_flags, d_counts, stream
+            )
+        )
+
+    def pack_records_device(self, d_recs: int, n: int, d_out: int, stream: int = 0):
+        self._ck(self.L.mscan_pack_records_device(self.h, d_recs, n, d_out, stream))
 
     def segments_device(self, video_off, durations, d_pts, d_flags, d_segs, d_res, stream: int = 0):
         video_off = np.ascontiguousarray(video_off, dtype=np.uint64)

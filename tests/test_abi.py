@@ -25,7 +25,7 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(L, n), f"{n} declared in motionscan.h but not exported"
         assert n in ms.SYMBOLS, f"{n} has no ctypes prototype"
-    assert L.mscan_abi_version() == 1
+    assert L.mscan_abi_version() == 2
 
 
 def test_struct_layouts():
@@ -33,7 +33,8 @@ def test_struct_layouts():
     assert C.sizeof(ms.Params) == 56
     assert C.sizeof(ms.Geometry) == 16
     assert C.sizeof(ms.VideoResult) == 40 and ms.RESULT_DTYPE.itemsize == 40
-    assert C.sizeof(ms.Stats) == 72
+    assert C.sizeof(ms.Stats) == 88
+    assert ms.MV8_DTYPE.itemsize == 8
     assert C.sizeof(ms.MvgenSpec) == 88
 
 
@@ -80,3 +81,19 @@ def test_host_generator_deterministic_and_structured():
     # padding bytes are zero so host and device generators can be compared byte-wise
     raw = recs.view(np.uint8).reshape(-1, 40)
     assert not raw[:, 14:16].any() and not raw[:, 34:40].any()
+
+
+def test_pack_records_is_the_byte_range_6_to_14():
+    """mscan_pack_records (no GPU needed): out[i] == bytes [6,14) of recs[i] == (src_x, src_y, dst_x, dst_y)."""
+    rng = np.random.default_rng(7)
+    for n in (0, 1, 7, 4096, 100_003):
+        raw = rng.integers(0, 256, size=(n, 40), dtype=np.uint8)
+        recs = raw.reshape(-1).view(ms.MV_DTYPE)
+        out = ms.pack_records(recs)
+        assert out.dtype == ms.MV8_DTYPE and len(out) == n
+        assert out.view(np.uint8).reshape(n, 8).tobytes() == raw[:, 6:14].tobytes()
+        for f in ("src_x", "src_y", "dst_x", "dst_y"):
+            assert np.array_equal(out[f], recs[f])
+    # misaligned output is refused, not silently mis-stored
+    buf = np.zeros(8 * 4 + 4, np.uint8)
+    assert ms.lib().mscan_pack_records(recs.ctypes.data, 4, buf.ctypes.data + 4) == ms.ERR_INVALID

@@ -1,0 +1,222 @@
+"""GPU: every way records can reach K-A gives the oracle's answer bit for bit.
+
+Feed modes (include/motionscan.h, mscan_set_staging_mode / mscan_submit_packed):
+  native-inplace   native 40-byte records in pinned memory, DMA'd in place        → K-A<native>
+  native-staged    native records in pageable memory, memcpy'd to staging (mode NATIVE) → K-A<native>
+  projected        native records in pageable memory, staging pass projects to 8 B (mode AUTO, default) → K-A<packed>
+  projected-pinned native records in pinned memory, projected anyway (mode PACK)   → K-A<packed>
+  packed-pinned    caller-projected mscan_mv8 in pinned memory, DMA'd in place     → K-A<packed>
+  packed-pageable  caller-projected mscan_mv8 in pageable memory                   → K-A<packed>
+"""
+import numpy as np
+import pytest
+
+import kats
+import motionscan as ms
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["native-inplace", "native-staged", "projected", "projected-pinned", "packed-pinned", "packed-pageable"]
+
+
+def cfg_for(p, w, h):
+    gw, gh, m = orc.geometry(w, h, p.block_size, p.block_shift, p.vertical_mask)
+    return orc.make_cfg(p, gw, gh, m)
+
+
+class Feeder:
+    """Submits (pts, cnt, recs) to a video in one of MODES; owns the pinned copies until close()."""
+
+    def __init__(self, ctx, mode):
+        self.ctx, self.mode, self.pinned = ctx, mode, []
+        ctx.set_staging_mode({"native-staged": ms.STAGING_NATIVE, "projected-pinned": ms.STAGING_PACK}.get(mode, ms.STAGING_AUTO))
+
+    def _pin(self, a):
+        h = self.ctx.pinned_array(max(len(a), 1), a.dtype)[: len(a)]
+        h[:] = a
+        self.pinned.append(h)
+        return h
+
+    def submit(self, vid, pts, cnt, recs):
+        if recs is None:
+            recs = np.zeros(0, ms.MV_DTYPE)
+        m = self.mode
+        if m in ("native-inplace", "projected-pinned"):
+            return self.ctx.submit(vid, pts, cnt, self._pin(recs))
+        if m in ("native-staged", "projected"):
+            return self.ctx.submit(vid, pts, cnt, recs)
+        r8 = ms.pack_records(recs)
+        return self.ctx.submit_packed(vid, pts, cnt, self._pin(r8) if m == "packed-pinned" else r8)
+
+    def close(self):
+        self.ctx.host_fence()
+        for h in self.pinned:  # views starting at the allocation's first byte
+            self.ctx.host_free(h.ctypes.data)
+        self.pinned = []
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_frame_kats_every_feed_mode(mode):
+    K = kats.frame_kats()
+    groups = {}
+    for name, (p, recs, flag, count) in K.items():
+        key = (p.mv_threshold_sq, p.vectors_needed, p.clusters_needed)
+        groups.setdefault(key, (p, []))[1].append((name, recs, flag, count))
+    for p, items in groups.values():
+        with ms.Context(0, p) as ctx:
+            fd = Feeder(ctx, mode)
+            frames = [r for _, r, _, _ in items]
+            cnt = np.array([0 if f is None else len(f) for f in frames], dtype=np.uint32)
+            recs = kats.cat(*[f for f in frames if f is not None and len(f)])
+            ctx.video_open(1, kats.W, kats.H)
+            fd.submit(1, np.arange(len(frames)) / 30.0, cnt, recs)
+            flags, counts = ctx.collect(1)
+            fd.close()
+        for i, (name, _, flag, count) in enumerate(items):
+            assert flags[i] == flag, (mode, name)
+            assert counts[i] == count, (mode, name)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("seed", range(3))
+def test_random_ragged_frames_every_feed_mode(mode, seed):
+    """Ragged frames whose sizes sit on and around the ring-stage boundaries of both layouts (512 native /
+    2560 packed records per stage), starting at odd record indices (the 8-byte phase inside a 16-byte copy)."""
+    from test_oracle_kats import random_frame
+
+    rng = np.random.default_rng(4200 + seed)
+    w, h = [(1920, 1080), (3840, 2160), (640, 360)][seed]
+    p = kats.env_params() if seed != 1 else kats.code_defaults()
+    p.vectors_needed = int(rng.integers(1, 5))
+    p.clusters_needed = int(rng.integers(1, 4))
+    sizes = [1, 0, 511, 512, 513, 3, 2559, 2560, 2561, 0, 5119, 5120, 5121, 7, 7679, 7680, 7681, 1023, 20479, 2, 10241]
+    sizes += [int(x) for x in rng.integers(0, 9000, 20)]
+    frames = [random_frame(rng, n, w, h, int(rng.integers(1, 6))) if n else None for n in sizes]
+    cnt = np.array(sizes, dtype=np.uint32)
+    recs = kats.cat(*[f for f in frames if f is not None])
+    pts = np.arange(len(sizes)) / 25.0
+    cfg = cfg_for(p, w, h)
+    with ms.Context(0, p) as ctx:
+        fd = Feeder(ctx, mode)
+        ctx.video_open(5, w, h)
+        fd.submit(5, pts, cnt, recs)
+        flags, counts = ctx.collect(5)
+        fd.close()
+    for i, f in enumerate(frames):
+        assert counts[i] == orc.full_count(cfg, f), (mode, i, sizes[i])
+        assert flags[i] == orc.check_frame(cfg, f), (mode, i, sizes[i])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_synthetic_clip_every_feed_mode(mode):
+    """configs[0]-style 1080p clip through each feed mode, tiny slabs so frames span many launches;
+    flags, full counts, segments and decision bit-exact."""
+    spec = ms.synth_preset(0, 21)
+    n = 420
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    p = kats.env_params()
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    osegs, ores = orc.video_tail(pts, of, n / spec.fps, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+    with ms.Context(0, p, 0, 4 << 20) as ctx:
+        fd = Feeder(ctx, mode)
+        ctx.video_open(2, spec.width, spec.height)
+        for a in range(0, n, 53):
+            b = min(n, a + 53)
+            fd.submit(2, pts[a:b], cnt[a:b], recs[int(off[a]) : int(off[b])])
+        flags, counts = ctx.collect(2)
+        segs, res = ctx.motion_segments(2, n / spec.fps)
+        st = ctx.stats()
+        fd.close()
+    assert np.array_equal(counts, oc) and np.array_equal(flags, of)
+    assert res.decision == ores.decision and segs.tobytes() == osegs.tobytes()
+    assert np.float64(res.saved_pct).tobytes() == np.float64(ores.saved_pct).tobytes()
+    n_rec = int(off[-1])
+    if mode.startswith("native"):
+        assert st.h2d_bytes >= 40 * n_rec and st.records_projected == 0
+    else:
+        assert 8 * n_rec <= st.h2d_bytes < 9 * n_rec  # 8 B/record + per-frame metadata cross PCIe
+        assert st.records_projected == (n_rec if mode.startswith("projected") else 0)
+
+
+def test_formats_mixed_inside_one_video():
+    """Chunk workers of one video may feed different formats; a slab never mixes them."""
+    spec = ms.synth_preset(3, 9)
+    n = 240
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    p = kats.env_params()
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    with ms.Context(0, p, 0, 16 << 20) as ctx:
+        hp = ctx.pinned_array(len(recs), ms.MV_DTYPE)
+        hp[:] = recs
+        r8 = ms.pack_records(recs)
+        ctx.video_open(1, spec.width, spec.height)
+        for k, a in enumerate(range(0, n, 20)):
+            b = a + 20
+            r0, r1 = int(off[a]), int(off[b])
+            if k % 3 == 0:
+                ctx.submit(1, pts[a:b], cnt[a:b], hp[r0:r1])       # native, in place
+            elif k % 3 == 1:
+                ctx.submit(1, pts[a:b], cnt[a:b], recs[r0:r1])     # projected by the staging pass
+            else:
+                ctx.submit_packed(1, pts[a:b], cnt[a:b], r8[r0:r1])  # caller-projected
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+        ctx.host_free(hp.ctypes.data)
+    assert np.array_equal(counts, oc) and np.array_equal(flags, of)
+    assert st.scan_launches >= 8  # every format switch closes the slab
+
+
+@pytest.mark.parametrize("threads", [1, 3, 0])
+def test_large_submit_uses_the_projection_pool(threads):
+    """One submit of > 256 Ki records is projected by the pool (any size of it) with identical results."""
+    spec = ms.synth_preset(2, 31)  # 4K dense: 129 600 records per P-frame
+    n = 14
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    assert int(off[-1]) > 1 << 20
+    p = kats.env_params()
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    with ms.Context(0, p) as ctx:
+        ctx.set_pack_threads(threads)
+        ctx.video_open(1, spec.width, spec.height)
+        ctx.submit(1, pts, cnt, recs)
+        ctx.submit(1, pts + 1.0, cnt, recs)  # pool reused for a second job
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+    assert np.array_equal(counts, np.concatenate([oc, oc])) and np.array_equal(flags, np.concatenate([of, of]))
+    assert st.records_projected == 2 * int(off[-1]) and st.project_ms > 0
+
+
+def test_scan_device_packed_matches_native():
+    """Device-resident: K-A<packed> on the projection of a stream == K-A<native> on the stream == oracle."""
+    spec = ms.synth_preset(1, 3)
+    n = 900
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    r8 = ms.pack_records(recs)
+    p = kats.env_params()
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    with ms.Context(0, p) as ctx:
+        d_recs = ctx.dev_alloc(recs.nbytes + 256)
+        d_r8 = ctx.dev_alloc(r8.nbytes + 256)
+        d_off = ctx.dev_alloc(off.nbytes)
+        d_flags, d_counts = ctx.dev_alloc(n), ctx.dev_alloc(4 * n)
+        ctx.h2d(d_recs, recs)
+        ctx.pack_records_device(d_recs, len(recs), d_r8)  # device projection == host projection
+        ctx.sync()
+        back = np.zeros(len(recs), ms.MV8_DTYPE)
+        ctx.d2h(back, d_r8)
+        assert back.tobytes() == r8.tobytes()
+        ctx.h2d(d_off, off)
+        geom = ms.geometry_from_dims(p, spec.width, spec.height)
+        out = []
+        for fn, d in ((ctx.scan_device, d_recs), (ctx.scan_device_packed, d_r8)):
+            fn(d, d_off, None, [geom], n, d_flags, d_counts)
+            ctx.sync()
+            f, c = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+            ctx.d2h(f, d_flags)
+            ctx.d2h(c, d_counts)
+            out.append((f, c))
+        for d in (d_recs, d_r8, d_off, d_flags, d_counts):
+            ctx.dev_free(d)
+    for f, c in out:
+        assert np.array_equal(c, oc) and np.array_equal(f, of)
