@@ -6,10 +6,14 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "memory_io.hpp"
 #include "motionscan.h"
+#ifdef MT_WITH_FFMPEG
+#include "ffmpeg_frontend.hpp"
+#endif
 
 namespace motion_trim {
 
@@ -23,8 +27,12 @@ class MotionScanner {
   bool initialize();
   double get_duration();  // fmt_ctx->duration / AV_TIME_BASE, or 0.0 (src/motion_scanner.cpp:204-208)
   double get_fps();       // avg_frame_rate, 25.0 when unknown (:210-215)
-  int width() const { return view_.width; }
-  int height() const { return view_.height; }
+  int width() const;
+  int height() const;
+  // Which producer feeds the GPU: the zero-copy MVS1 view, or (MT_WITH_FFMPEG builds) FFmpeg demux +
+  // export_mvs decode. MOTION_TRIM_FRONTEND=ffmpeg|mvs forces one; by default MVS1 files take the view
+  // and everything else goes to FFmpeg.
+  bool uses_ffmpeg() const { return use_ffmpeg_; }
 
   // Contract-compatible: submits the range, waits for the GPU and returns the pts with motion.
   std::vector<double> scan_range(double start, double end, long& seek_us, long& decode_us, long& analyze_us);
@@ -38,6 +46,11 @@ class MotionScanner {
   uint32_t video_id_;
   MvsView view_;
   bool ready_ = false;
+  bool use_ffmpeg_ = false;
+#ifdef MT_WITH_FFMPEG
+  std::unique_ptr<FFmpegFrontEnd> ff_;
+  long scan_range_ffmpeg(double start, double end, long& seek_us, long& decode_us, uint64_t* first_frame);
+#endif
   struct Run {
     uint64_t first;  // index in the video's submission order
     uint32_t n;

@@ -1,7 +1,8 @@
 // main.cpp — motion_trim_b200 <input> <output>: same two positionals and the same directory/file switch
 // as the reference CLI (src/main.cpp:35-100). A directory ⇒ batch over the GPUs of the box, a file ⇒
 // single pipeline on GPU 0. Inputs are MVS1 motion-vector stream files (.mvs) — what FFmpeg's
-// export_mvs decode of the clip would deliver; the image has no FFmpeg to decode media itself.
+// export_mvs decode of the clip would deliver — and, in -DMT_WITH_FFMPEG builds, the media files the
+// reference accepts (src/main.cpp:68-69), decoded by the FFmpeg front-end.
 // `--print-segments` additionally prints the decision and the job's segments as hex doubles.
 #include <algorithm>
 #include <cstdio>
@@ -17,6 +18,15 @@
 
 namespace fs = std::filesystem;
 using namespace motion_trim;
+
+static bool accepted(const std::string& ext) {
+  if (ext == ".mvs") return true;
+#ifdef MT_WITH_FFMPEG
+  for (const char* m : {".mp4", ".mkv", ".ts", ".mov", ".avi"})  // src/main.cpp:68-69
+    if (ext == m) return true;
+#endif
+  return false;
+}
 
 int main(int argc, char** argv) {
   std::setvbuf(stdout, nullptr, _IONBF, 0);
@@ -34,7 +44,7 @@ int main(int argc, char** argv) {
   if (fs::is_directory(input)) {
     std::vector<std::string> files;
     for (const auto& e : fs::directory_iterator(input))
-      if (e.is_regular_file() && e.path().extension() == ".mvs") files.push_back(e.path().string());
+      if (e.is_regular_file() && accepted(e.path().extension().string())) files.push_back(e.path().string());
     std::sort(files.begin(), files.end());
     if (!fs::exists(output)) fs::create_directories(output);
     BatchProcessor batch(Config::parallel_streams());

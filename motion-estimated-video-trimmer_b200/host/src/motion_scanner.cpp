@@ -6,6 +6,8 @@
 #include "motion_trim/motion_scanner.hpp"
 
 #include <chrono>
+#include <cstdlib>
+#include <cstring>
 
 #include "motion_trim/config.hpp"
 
@@ -21,16 +23,86 @@ MotionScanner::MotionScanner(const MappedFile& data, mscan_ctx* gpu, uint32_t vi
     : file_(data), gpu_(gpu), video_id_(video_id) {}
 
 bool MotionScanner::initialize() {
-  ready_ = view_.parse(file_) && gpu_ != nullptr;
+  ready_ = false;
+  if (!gpu_) return false;
+  const char* want = std::getenv("MOTION_TRIM_FRONTEND");
+  const bool force_ff = want && !std::strcmp(want, "ffmpeg"), force_mvs = want && !std::strcmp(want, "mvs");
+  if (!force_ff && view_.parse(file_)) {
+    use_ffmpeg_ = false;
+    ready_ = true;
+    return true;
+  }
+  if (force_mvs) return false;
+#ifdef MT_WITH_FFMPEG
+  ff_ = std::make_unique<FFmpegFrontEnd>(file_);
+  use_ffmpeg_ = ready_ = ff_->open();
+  if (!ready_) ff_.reset();
   return ready_;
+#else
+  return false;  // media files need a build with -DMT_WITH_FFMPEG
+#endif
 }
 
-double MotionScanner::get_duration() { return ready_ ? view_.duration_us / 1000000.0 : 0.0; }
+double MotionScanner::get_duration() {
+  if (!ready_) return 0.0;
+#ifdef MT_WITH_FFMPEG
+  if (use_ffmpeg_) return ff_->duration();
+#endif
+  return view_.duration_us / 1000000.0;
+}
 
-double MotionScanner::get_fps() { return (ready_ && view_.fps_den > 0 && view_.fps_num > 0) ? view_.fps_num / (double)view_.fps_den : 25.0; }
+double MotionScanner::get_fps() {
+#ifdef MT_WITH_FFMPEG
+  if (ready_ && use_ffmpeg_) return ff_->fps();
+#endif
+  return (ready_ && view_.fps_den > 0 && view_.fps_num > 0) ? view_.fps_num / (double)view_.fps_den : 25.0;
+}
+
+int MotionScanner::width() const {
+#ifdef MT_WITH_FFMPEG
+  if (use_ffmpeg_ && ff_) return ff_->width();
+#endif
+  return view_.width;
+}
+
+int MotionScanner::height() const {
+#ifdef MT_WITH_FFMPEG
+  if (use_ffmpeg_ && ff_) return ff_->height();
+#endif
+  return view_.height;
+}
+
+#ifdef MT_WITH_FFMPEG
+// Decode-fed variant: every batch of projected frames the front-end stages becomes one mscan_submit_packed.
+long MotionScanner::scan_range_ffmpeg(double start, double end, long& seek_us, long& decode_us, uint64_t* first_frame) {
+  pts_.clear();
+  runs_.clear();
+  long stage_us = 0;
+  bool failed = false;
+  const long n = ff_->scan(start, end, seek_us, decode_us, stage_us, size_t(1) << 20, [&](const StagedFrames& b) {
+    uint64_t idx = 0;
+    const int rc = mscan_submit_packed(gpu_, video_id_, (uint32_t)b.pts.size(), b.pts.data(), b.counts.data(),
+                                       b.recs.empty() ? nullptr : b.recs.data(), &idx);
+    if (rc != MSCAN_OK) {
+      failed = true;
+      return false;
+    }
+    runs_.push_back(Run{idx, (uint32_t)b.pts.size(), pts_.size()});
+    pts_.insert(pts_.end(), b.pts.begin(), b.pts.end());
+    return true;
+  });
+  decode_us += stage_us;  // staging is part of what the worker does per decoded frame
+  if (failed || n < 0) return -1;
+  if (first_frame) *first_frame = runs_.empty() ? 0 : runs_.front().first;
+  return n;
+}
+#endif
 
 long MotionScanner::scan_range_async(double start, double end, long& seek_us, long& decode_us, uint64_t* first_frame) {
   if (!ready_) return -1;
+#ifdef MT_WITH_FFMPEG
+  if (use_ffmpeg_) return scan_range_ffmpeg(start, end, seek_us, decode_us, first_frame);
+#endif
   const double time_base = view_.tb_num / (double)view_.tb_den;  // av_q2d (:304-305)
   const double video_fps = get_fps();
   const double target = Config::target_fps();

@@ -53,16 +53,22 @@ int ProcessingPipeline::run() {
   const uint32_t video_id = pool_->next_video_id();
   double fps = 0;
   int width = 0, height = 0;
+  bool decode_fed = false;
   {
     MotionScanner probe(file_buffer_, gpu, video_id);
     if (!probe.initialize()) {
-      logf(stream_id_, "[ERROR] ", "Failed to initialize probe (not an MVS1 motion-vector stream?)");
+#ifdef MT_WITH_FFMPEG
+      logf(stream_id_, "[ERROR] ", "Failed to initialize probe (neither an MVS1 stream nor media FFmpeg can open)");
+#else
+      logf(stream_id_, "[ERROR] ", "Failed to initialize probe (not an MVS1 motion-vector stream; media files need a -DMT_WITH_FFMPEG build)");
+#endif
       return 1;
     }
     duration_ = probe.get_duration();
     fps = probe.get_fps();
     width = probe.width();
     height = probe.height();
+    decode_fed = probe.uses_ffmpeg();
   }
   if (!(duration_ > 0)) {  // the reference divides by zero here (pipeline.cpp:141-143,259); refuse instead
     logf(stream_id_, "[ERROR] ", "stream has no duration");
@@ -71,7 +77,8 @@ int ProcessingPipeline::run() {
   // Pin the mapped stream so mscan_submit DMAs records straight out of the page cache; if the platform
   // refuses (or MOTION_TRIM_NO_PIN is set) submits fall back to the library's pinned staging copy.
   bool registered = false;
-  if (!std::getenv("MOTION_TRIM_NO_PIN"))
+  // (decode-fed runs stage projected records instead: nothing is DMA'd out of the media file)
+  if (!decode_fed && !std::getenv("MOTION_TRIM_NO_PIN"))
     registered = mscan_host_register(gpu, const_cast<uint8_t*>(file_buffer_.data()), file_buffer_.size(), 1) == MSCAN_OK;
   struct Unpin {
     mscan_ctx* g;
@@ -89,7 +96,7 @@ int ProcessingPipeline::run() {
   }
   char buf[160];
   std::snprintf(buf, sizeof buf, "Duration: %.2fs (%.0f frames @ %.1ffps) on GPU %d%s", duration_, duration_ * fps, fps, gpu_index_,
-                registered ? ", input pinned for in-place DMA" : "");
+                decode_fed ? ", FFmpeg export_mvs front-end" : registered ? ", input pinned for in-place DMA" : "");
   logf(stream_id_, "[INFO] ", buf);
 
   // ---- chunk queue + workers (the workers are the decode front-end; here they walk the MVS index)

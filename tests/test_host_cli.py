@@ -30,13 +30,13 @@ def write_case(c, path):
                      tb_num=c.tb[0], tb_den=c.tb[1], duration_us=c.duration_us)
 
 
-def run_cli(args, params, chunk_sec=None, threads=None, extra_env=None, target_fps=None):
+def run_cli(args, params, chunk_sec=None, threads=None, extra_env=None, target_fps=None, binary=None):
     env = dict(os.environ)
     env.update(ref_runner.env_for(params, chunk_sec, target_fps))
     if threads:
         env["THREADS_PER_STREAM"] = str(threads)
     env.update(extra_env or {})
-    return subprocess.run([str(BIN), *args], env=env, capture_output=True, text=True, timeout=300)
+    return subprocess.run([str(binary or BIN), *args], env=env, capture_output=True, text=True, timeout=300)
 
 
 def parse(stdout):
