@@ -356,7 +356,7 @@ uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, u
 
 }  // namespace
 
-bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan) {
+bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, bool packed, ScanPlan* plan) {
   const uint32_t b32 = max_cells * 4u, b16 = ((max_cells + 1u) / 2u) * 4u;
   auto set = [&](uint32_t ctas, uint32_t st, uint32_t cnt16, uint32_t global_cnt) {
     plan->stages = st;
@@ -373,11 +373,22 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
     if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st)) {
       set(want_ctas, want_st, c16, 0);
       const uint32_t w = env_u32("MSCAN_KA_WARPS");
-      if (w == 8 || (w == 16 && want_ctas == 1)) plan->cons_warps = w;
+      if (w == 8 || w == 16) plan->cons_warps = w;
       return true;
     }
   }
   uint32_t st;
+  if (packed) {
+    // Projected records carry 5x fewer bytes per vote: K-A<packed> is bound by instruction issue, not by
+    // HBM, so the plan buys resident warps with ring depth (sweep: profiles/r02_ka_sweep_packed.log —
+    // 1080p 3 CTAs x 8 warps x 2 stages 420 G rec/s vs 326 for the native plan; 4K 2 x 16 x 2 431 vs 346)
+    if ((st = fit_stages(3, b16, max_bit_words, smem_optin, 2, 2))) return set(3, st, 1, 0);
+    if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 2, 2))) {
+      set(2, st, 1, 0);
+      plan->cons_warps = 16;
+      return true;
+    }
+  }
   // 1-4: two CTAs per SM; a 4-stage ring (160 KB in flight per SM) measures ~1.3 % faster than 3 stages
   // (tools/ka_sweep.py), so 16-bit counters are preferred when they are what makes the 4th stage fit
   if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4))) return set(2, st, 0, 0);

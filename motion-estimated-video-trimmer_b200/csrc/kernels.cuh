@@ -49,8 +49,8 @@ struct ScanPlan {
   uint32_t cnt16;       // 16-bit shared-memory counters (half the footprint, guarded against carry)
 };
 
-// Chooses ring depth / occupancy for the largest geometry; false if it cannot fit.
-bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, ScanPlan* plan);
+// Chooses ring depth / occupancy for the largest geometry and the record layout; false if it cannot fit.
+bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, bool packed, ScanPlan* plan);
 cudaError_t scan_configure(uint32_t smem_optin);
 uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames);
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st);

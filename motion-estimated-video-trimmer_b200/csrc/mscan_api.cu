@@ -225,7 +225,8 @@ struct mscan_ctx {
   std::vector<DevGeom> geoms;
   DevGeom* d_geoms = nullptr;
   uint32_t max_cells = 0, max_bit_words = 0;
-  ScanPlan plan{};
+  ScanPlan plan{};         // native 40-byte slabs
+  ScanPlan plan_packed{};  // mscan_mv8 slabs
 
   // frame log
   uint64_t log_cap = 0, log_head = 0;
@@ -430,10 +431,11 @@ int launch_slab(mscan_ctx* c, Slab& s) {
   a.flags = c->d_flags + s.log_base;
   a.counts = c->d_counts + s.log_base;
   a.n_frames = s.frames;
-  a.stages = c->plan.stages;
+  const ScanPlan& plan = s.packed ? c->plan_packed : c->plan;
+  a.stages = plan.stages;
   a.max_cells = c->max_cells;
   a.max_bit_words = c->max_bit_words;
-  int rc = run_scan(c, a, c->plan, s.stream, s.recs);
+  int rc = run_scan(c, a, plan, s.stream, s.recs);
   if (rc) return rc;
   CU(cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
@@ -477,12 +479,14 @@ int sync_scans_locked(mscan_ctx* c) {
 }
 
 int replan(mscan_ctx* c) {
-  ScanPlan p;
-  if (!scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, &p))
+  ScanPlan p, pp;
+  if (!scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, false, &p) ||
+      !scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, true, &pp))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells: bit-rows do not fit shared memory", c->max_cells);
   if (p.global_cnt && (uint64_t)c->num_sms * p.ctas_per_sm * c->max_cells * sizeof(uint32_t) > (16ull << 30))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells needs more than 16 GiB of counter scratch", c->max_cells);
   c->plan = p;
+  c->plan_packed = pp;
   return MSCAN_OK;
 }
 
@@ -1345,7 +1349,7 @@ static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const
     words = std::max(words, wo);
   }
   ScanPlan plan;
-  if (!scan_plan(cells, words, c->smem_optin, &plan))
+  if (!scan_plan(cells, words, c->smem_optin, packed, &plan))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells does not fit shared memory", cells);
   if (n_geoms > c->user_geoms_cap) {
     cudaFree(c->d_user_geoms);

@@ -12,7 +12,10 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent.parent
-LIB_PATH = PKG_DIR / "libmotionscan.so"
+import os
+
+# MSCAN_LIB: load another build of the same library (kernel tuning experiments, tools/ka_sweep.py)
+LIB_PATH = Path(os.environ["MSCAN_LIB"]) if os.environ.get("MSCAN_LIB") else PKG_DIR / "libmotionscan.so"
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_CAPACITY, ERR_UNSUPPORTED = range(6)
 NO_MOTION, CUT, FULL_COPY = 0, 1, 2
