@@ -501,6 +501,7 @@ def run_gpu(args):
         if mode == "projected":
             modes[mode]["host_threads"] = pack_threads
             modes[mode]["project_ms_per_step"] = est.project_ms / e2e_steps
+            modes[mode]["records_projected_per_step"] = int(est.records_projected // e2e_steps)
     ctx.set_staging_mode(ms.STAGING_AUTO)
     e2e_mode = max(("native_inplace", "projected"), key=lambda m: modes[m]["value"])
     best = modes[e2e_mode]
@@ -577,8 +578,8 @@ def run_gpu(args):
                 "modes": modes,
                 "how": "per step: mscan_video_open / mscan_submit of native 40-B host records / collect / segments_batch / close; "
                 "value = best of native_inplace (pinned records DMA'd in place, 40 B/record over PCIe) and projected (the "
-                "library's staging pass keeps the 8 bytes the path reads, 8 B/record over PCIe); packed_pinned (caller-projected "
-                "records) is reported in modes only",
+                "library's staging pass keeps the 8 bytes the path reads, 8 B/record over PCIe); "
+                "packed_pinned (caller-projected records) is reported in modes only",
             },
             "packed_kernel": packed,
             "cpu_baseline": cpu,

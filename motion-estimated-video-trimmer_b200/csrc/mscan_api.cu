@@ -69,11 +69,16 @@ struct Slab {
   cudaEvent_t done = nullptr;
   cudaEvent_t copied = nullptr;  // recorded after the slab's last H2D copy (mscan_host_fence)
   bool in_flight = false;
-  bool packed = false;  // the slab holds mscan_mv8 projections (8 B) instead of native records (40 B)
-  uint64_t bytes = 0;
-  uint64_t recs = 0;
-  uint32_t frames = 0;
-  uint64_t log_base = 0;
+  uint64_t bytes = 0;   // fill level of d_recs (and of h_recs, which mirrors its offsets)
+  uint32_t frames = 0;  // frames staged since the slab was recycled
+  // The open segment = frames [seg_frame0, frames): one record format, one K-A launch. A slab carries any
+  // number of segments (chunk workers may feed different formats); they are launched in order on `stream`.
+  bool packed = false;        // the open segment holds mscan_mv8 projections (8 B), not native records (40 B)
+  uint32_t seg_frame0 = 0;
+  uint32_t seg_slot0 = 0;     // first rec_off slot of the open segment (a segment of k frames uses k+1 slots)
+  uint64_t seg_byte0 = 0;     // 256-byte aligned offset of the open segment's first record
+  uint64_t seg_recs = 0;
+  uint64_t seg_log_base = 0;  // frame-log index of the open segment's first frame
 };
 
 struct EvPair {
@@ -413,33 +418,48 @@ ScanArgs base_args(mscan_ctx* c) {
   return a;
 }
 
-// launch K-A on whatever the current slab holds
-int launch_slab(mscan_ctx* c, Slab& s) {
-  if (s.frames == 0) return MSCAN_OK;
-  s.h_rec_off[s.frames] = s.recs;
-  CU(cudaMemcpyAsync(s.d_rec_off, s.h_rec_off, sizeof(uint64_t) * (s.frames + 1), cudaMemcpyHostToDevice, s.stream));
-  CU(cudaMemcpyAsync(s.d_geom, s.h_geom, sizeof(uint32_t) * s.frames, cudaMemcpyHostToDevice, s.stream));
-  CU(cudaMemcpyAsync(c->d_pts + s.log_base, s.h_pts, sizeof(double) * s.frames, cudaMemcpyHostToDevice, s.stream));
-  c->stats.h2d_bytes += sizeof(uint64_t) * (s.frames + 1) + 12ull * s.frames;
-  CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of this slab precedes this point
+// launch K-A on the open segment of a slab and open the next one
+int launch_segment(mscan_ctx* c, Slab& s) {
+  const uint32_t n = s.frames - s.seg_frame0;
+  if (n == 0) return MSCAN_OK;
+  s.h_rec_off[s.seg_slot0 + n] = s.seg_recs;
+  CU(cudaMemcpyAsync(s.d_rec_off + s.seg_slot0, s.h_rec_off + s.seg_slot0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(s.d_geom + s.seg_frame0, s.h_geom + s.seg_frame0, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s.stream));
+  CU(cudaMemcpyAsync(c->d_pts + s.seg_log_base, s.h_pts + s.seg_frame0, sizeof(double) * n, cudaMemcpyHostToDevice, s.stream));
+  c->stats.h2d_bytes += sizeof(uint64_t) * (n + 1) + 12ull * n;
+  CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of the slab so far precedes this point
   ScanArgs a = base_args(c);
-  a.recs = s.d_recs;
+  a.recs = s.d_recs + s.seg_byte0;
   a.packed = s.packed ? 1u : 0u;
-  a.rec_off = s.d_rec_off;
-  a.frame_geom = s.d_geom;
+  a.rec_off = s.d_rec_off + s.seg_slot0;
+  a.frame_geom = s.d_geom + s.seg_frame0;
   a.geoms = c->d_geoms;
-  a.flags = c->d_flags + s.log_base;
-  a.counts = c->d_counts + s.log_base;
-  a.n_frames = s.frames;
+  a.flags = c->d_flags + s.seg_log_base;
+  a.counts = c->d_counts + s.seg_log_base;
+  a.n_frames = n;
   const ScanPlan& plan = s.packed ? c->plan_packed : c->plan;
   a.stages = plan.stages;
   a.max_cells = c->max_cells;
   a.max_bit_words = c->max_bit_words;
-  int rc = run_scan(c, a, plan, s.stream, s.recs);
+  int rc = run_scan(c, a, plan, s.stream, s.seg_recs);
   if (rc) return rc;
   CU(cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
+  s.seg_frame0 = s.frames;
+  s.seg_slot0 += n + 1;
+  s.bytes = (s.bytes + 255) & ~255ull;
+  s.seg_byte0 = s.bytes;
+  s.seg_recs = 0;
   return MSCAN_OK;
+}
+
+void recycle_slab(Slab& s) {
+  s.bytes = 0;
+  s.frames = 0;
+  s.seg_frame0 = 0;
+  s.seg_slot0 = 0;
+  s.seg_byte0 = 0;
+  s.seg_recs = 0;
 }
 
 int wait_slab(mscan_ctx* c, Slab& s) {
@@ -447,16 +467,15 @@ int wait_slab(mscan_ctx* c, Slab& s) {
     CU(cudaEventSynchronize(s.done));
     s.in_flight = false;
   }
-  s.bytes = 0;
-  s.recs = 0;
-  s.frames = 0;
+  recycle_slab(s);
   return MSCAN_OK;
 }
 
+// launch what the current slab holds and move on to the next slab of the ring
 int flush_locked(mscan_ctx* c) {
   Slab& s = c->slabs[c->cur];
-  if (s.frames == 0 || s.in_flight) return MSCAN_OK;
-  int rc = launch_slab(c, s);
+  if (s.frames == 0) return MSCAN_OK;
+  int rc = launch_segment(c, s);
   if (rc) return rc;
   c->cur = (c->cur + 1) % kSlabs;
   return wait_slab(c, c->slabs[c->cur]);
@@ -469,11 +488,7 @@ int sync_scans_locked(mscan_ctx* c) {
     if (s.in_flight) {
       CU(cudaEventSynchronize(s.done));
       s.in_flight = false;
-      if (&s != &c->slabs[c->cur]) {
-        s.bytes = 0;
-        s.recs = 0;
-        s.frames = 0;
-      }
+      if (&s != &c->slabs[c->cur]) recycle_slab(s);
     }
   return MSCAN_OK;
 }
@@ -708,9 +723,9 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CUB_(cudaMalloc((void**)&s.d_recs, c->slab_bytes + 256));
-    CUB_(cudaMalloc((void**)&s.d_rec_off, sizeof(uint64_t) * (c->slab_frames + 1)));
+    CUB_(cudaMalloc((void**)&s.d_rec_off, sizeof(uint64_t) * (2 * (size_t)c->slab_frames + 2)));  // k+1 slots per segment
     CUB_(cudaMalloc((void**)&s.d_geom, sizeof(uint32_t) * c->slab_frames));
-    CUB_(cudaHostAlloc((void**)&s.h_rec_off, sizeof(uint64_t) * (c->slab_frames + 1), cudaHostAllocDefault));
+    CUB_(cudaHostAlloc((void**)&s.h_rec_off, sizeof(uint64_t) * (2 * (size_t)c->slab_frames + 2), cudaHostAllocDefault));
     CUB_(cudaHostAlloc((void**)&s.h_geom, sizeof(uint32_t) * c->slab_frames, cudaHostAllocDefault));
     CUB_(cudaHostAlloc((void**)&s.h_pts, sizeof(double) * c->slab_frames, cudaHostAllocDefault));
   }
@@ -891,10 +906,9 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   uint64_t src_rec = 0;
   while (f < n_frames) {
     Slab* s = &c->slabs[c->cur];
-    if (s->frames && s->packed != slab_packed) {  // one record format per slab (one K-A launch)
-      int rc = flush_locked(c);
+    if (s->frames > s->seg_frame0 && s->packed != slab_packed) {  // one record format per segment (K-A launch)
+      int rc = launch_segment(c, *s);
       if (rc) return rc;
-      continue;
     }
     // how many whole frames fit into the current slab
     uint32_t take = 0;
@@ -915,8 +929,8 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       if (rc) return rc;
       continue;
     }
-    if (s->frames == 0) {
-      s->log_base = c->log_head;
+    if (s->frames == s->seg_frame0) {
+      s->seg_log_base = c->log_head;
       s->packed = slab_packed;
     }
     const uint64_t nbytes = take_recs * out_stride;
@@ -949,9 +963,10 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       }
       c->stats.h2d_bytes += nbytes;
     }
-    uint64_t r = s->recs;
+    uint64_t r = s->seg_recs;
+    const uint32_t slot = s->seg_slot0 + (s->frames - s->seg_frame0);
     for (uint32_t i = 0; i < take; ++i) {
-      s->h_rec_off[s->frames + i] = r;
+      s->h_rec_off[slot + i] = r;
       r += rec_count[f + i];
       s->h_geom[s->frames + i] = v.geom;
       s->h_pts[s->frames + i] = pts[f + i];
@@ -963,7 +978,7 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     v.n_frames += take;
     c->log_head += take;
     s->frames += take;
-    s->recs += take_recs;
+    s->seg_recs += take_recs;
     s->bytes += nbytes;
     src_rec += take_recs;
     f += take;

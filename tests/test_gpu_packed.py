@@ -164,7 +164,7 @@ def test_formats_mixed_inside_one_video():
         st = ctx.stats()
         ctx.host_free(hp.ctypes.data)
     assert np.array_equal(counts, oc) and np.array_equal(flags, of)
-    assert st.scan_launches >= 8  # every format switch closes the slab
+    assert st.scan_launches >= 8  # every format switch closes a segment (one K-A launch each)
 
 
 @pytest.mark.parametrize("threads", [1, 3, 0])
@@ -220,3 +220,4 @@ def test_scan_device_packed_matches_native():
             ctx.dev_free(d)
     for f, c in out:
         assert np.array_equal(c, oc) and np.array_equal(f, of)
+
