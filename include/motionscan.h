@@ -143,6 +143,7 @@ typedef struct mscan_stats {
   double segment_ms;         /* Σ K-C durations, only while profiling is enabled         */
   uint64_t records_projected; /* native records the staging pass projected to mscan_mv8  */
   double project_ms;          /* host wall time spent in that projection                 */
+  uint64_t peer_bytes;        /* bytes mscan_video_append_from copied in from other contexts */
 } mscan_stats;
 
 typedef struct mscan_ctx mscan_ctx;
@@ -221,6 +222,12 @@ int mscan_segments_batch(mscan_ctx* ctx, uint32_t n_videos, const uint32_t* vide
                          const double* durations, mscan_segment* out, uint64_t cap,
                          uint64_t* seg_off_out, mscan_video_result* res_out);
 int mscan_video_close(mscan_ctx* ctx, uint32_t video_id);
+/* One long video split over several GPUs (each context scanned some of its chunks under its own video id):
+ * appends the per-frame results (pts, flag, full count) of (src, src_video) to (dst, dst_video) by a
+ * device-to-device copy — over NVLink when the two GPUs are peers — after which mscan_segments(dst, …) sees
+ * the whole video; the order of chunks does not matter (K-C sorts and de-duplicates like pipeline.cpp:302-304).
+ * src and dst may be the same context. The source video stays open and unchanged. */
+int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, uint32_t src_video);
 
 /* pinned host memory for zero-copy submit */
 int mscan_host_alloc(mscan_ctx* ctx, size_t bytes, void** p_out);

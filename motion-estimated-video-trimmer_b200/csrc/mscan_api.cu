@@ -1254,6 +1254,61 @@ int mscan_video_close(mscan_ctx* c, uint32_t video_id) {
   return MSCAN_OK;
 }
 
+// Cross-GPU stitch: the frames another context scanned for the same video join this
+// context's log by a peer copy of their 13 B/frame (NVLink when the GPUs are peers), so that K-C sees the
+// whole video. The union/sort/unique of chunk results (pipeline.cpp:268,302-304) then happens in K-C as usual.
+int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, uint32_t src_video) {
+  if (!dst || !src) return MSCAN_ERR_INVALID;
+  mscan_ctx* c = dst;  // errors are reported on the destination context
+  if (dst == src && dst_video == src_video) return fail(c, MSCAN_ERR_INVALID, "cannot append a video to itself");
+  std::unique_lock<std::mutex> l1(dst->mu, std::defer_lock), l2(src->mu, std::defer_lock);
+  if (dst == src) l1.lock();
+  else std::lock(l1, l2);
+  auto sit = src->videos.find(src_video);
+  if (sit == src->videos.end()) return fail(c, MSCAN_ERR_INVALID, "source video %u is not open", src_video);
+  auto dit = dst->videos.find(dst_video);
+  if (dit == dst->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", dst_video);
+  const Video& sv = sit->second;
+  Video& dv = dit->second;
+  if (sv.n_frames == 0) return MSCAN_OK;
+  if (dst->log_head + sv.n_frames > dst->log_cap)
+    return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames)", (unsigned long long)dst->log_cap);
+  // the source's results must exist; the destination's open segment must not straddle the imported range
+  if (cudaSetDevice(src->device) != cudaSuccess) return fail(c, MSCAN_ERR_CUDA, "cudaSetDevice(%d) failed", src->device);
+  {
+    mscan_ctx* c = src;  // CU() reports on `c`
+    int rc = sync_scans_locked(c);
+    if (rc) return fail(dst, rc, "source context: %s", src->err.c_str());
+  }
+  CU(cudaSetDevice(dst->device));
+  if (dst != src) {
+    int rc = launch_segment(dst, dst->slabs[dst->cur]);
+    if (rc) return rc;
+    if (dst->device != src->device) {  // best effort: direct NVLink path for the peer copies below
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) cudaDeviceEnablePeerAccess(src->device, 0);
+      cudaGetLastError();  // "already enabled" is fine
+    }
+  } else {
+    int rc = sync_scans_locked(dst);
+    if (rc) return rc;
+  }
+  uint64_t at = dst->log_head;
+  for (const Extent& e : sv.extents) {
+    CU(cudaMemcpyPeerAsync(dst->d_pts + at, dst->device, src->d_pts + e.start, src->device, sizeof(double) * e.n, dst->main_stream));
+    CU(cudaMemcpyPeerAsync(dst->d_flags + at, dst->device, src->d_flags + e.start, src->device, e.n, dst->main_stream));
+    CU(cudaMemcpyPeerAsync(dst->d_counts + at, dst->device, src->d_counts + e.start, src->device, sizeof(uint32_t) * e.n, dst->main_stream));
+    at += e.n;
+  }
+  CU(cudaStreamSynchronize(dst->main_stream));
+  dst->stats.peer_bytes += 13ull * sv.n_frames;
+  if (!dv.extents.empty() && dv.extents.back().start + dv.extents.back().n == dst->log_head) dv.extents.back().n += sv.n_frames;
+  else dv.extents.push_back(Extent{dst->log_head, sv.n_frames});
+  dv.n_frames += sv.n_frames;
+  dst->log_head += sv.n_frames;
+  return MSCAN_OK;
+}
+
 int mscan_host_alloc(mscan_ctx* c, size_t bytes, void** p) {
   if (!c || !p) return MSCAN_ERR_INVALID;
   CU(cudaSetDevice(c->device));

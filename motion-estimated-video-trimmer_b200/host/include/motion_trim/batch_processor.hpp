@@ -6,8 +6,11 @@
 #pragma once
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <queue>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -32,16 +35,28 @@ class BatchProcessor {
   int process(const std::vector<std::string>& input_files, const std::string& output_dir,
               const std::string& input_dir = "");
   const std::vector<StreamResult>& results() const { return results_; }
+  // Which directory entries are inputs (main.cpp passes its extension filter; used by watch mode).
+  void set_input_filter(std::function<bool(const std::string& ext)> f) { accept_ = std::move(f); }
+  // Ends watch mode (the reference has no way to: its stop flag is never set, batch_processor.cpp:180-183,240).
+  void stop_watch();
 
  private:
   bool next_file(std::string& out);
+  // WATCH_MODE=1 (reference src/batch_processor.cpp:237-305): poll the input directory every 2 s, enqueue
+  // files that are new, have no output yet and whose size was stable for 500 ms.
+  void monitor_directory(const std::string& input_dir, const std::string& output_dir);
   void stream_worker(int stream_id, int gpu, const std::string& output_dir);
 
   int streams_per_gpu_;
   GpuPool pool_;
   FFmpegQueue ffmpeg_queue_;
   std::mutex queue_mu_, results_mu_;
+  std::condition_variable queue_cv_;
   std::queue<std::string> work_;
+  std::set<std::string> seen_;  // watch mode: paths already enqueued or skipped
+  std::function<bool(const std::string&)> accept_;
+  std::atomic<bool> watching_{false}, stop_watch_{false};
+  std::atomic<int> in_progress_{0};
   std::vector<StreamResult> results_;
   std::atomic<int> failures_{0};
 };

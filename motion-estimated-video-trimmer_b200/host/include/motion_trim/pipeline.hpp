@@ -22,6 +22,10 @@ class ProcessingPipeline {
                      std::vector<int> cpu_set = {});
   // which GPU context scans this video (required before run())
   void set_gpu(GpuPool* pool, int gpu_index);
+  // Split this one video over several GPUs of the pool: chunk workers are bound to the
+  // GPUs round-robin, every GPU scans the chunks its workers pull, and the per-frame results are stitched
+  // on the first GPU (mscan_video_append_from, NVLink peer copy) before the segment step.
+  void set_gpus(GpuPool* pool, std::vector<int> gpu_indices);
   void set_ffmpeg_queue(FFmpegQueue* q) { ffmpeg_queue_ = q; }
 
   int run();  // 0 ok (including "no motion"), 1 failure — as the reference
@@ -45,7 +49,8 @@ class ProcessingPipeline {
   int num_threads_;
   std::vector<int> cpu_set_;
   GpuPool* pool_ = nullptr;
-  int gpu_index_ = 0;
+  int gpu_index_ = 0;              // the GPU that runs the segment step (first of gpus_)
+  std::vector<int> gpus_;          // all GPUs scanning this video
   FFmpegQueue* ffmpeg_queue_ = nullptr;
 };
 

@@ -4,9 +4,11 @@
 // the return value (:204-212). New: the stream threads are spread over the GPUs of the box.
 #include "motion_trim/batch_processor.hpp"
 
+#include <cctype>
 #include <chrono>
 #include <cstdio>
 #include <filesystem>
+#include <system_error>
 #include <thread>
 
 #include "motion_trim/config.hpp"
@@ -19,11 +21,61 @@ namespace motion_trim {
 BatchProcessor::BatchProcessor(int parallel_streams) : streams_per_gpu_(parallel_streams > 0 ? parallel_streams : 2) {}
 
 bool BatchProcessor::next_file(std::string& out) {
-  std::lock_guard<std::mutex> lk(queue_mu_);
+  std::unique_lock<std::mutex> lk(queue_mu_);
+  if (watching_) queue_cv_.wait(lk, [this] { return !work_.empty() || stop_watch_; });  // :218-227
   if (work_.empty()) return false;
   out = std::move(work_.front());
   work_.pop();
+  in_progress_++;
   return true;
+}
+
+void BatchProcessor::stop_watch() {
+  stop_watch_ = true;
+  queue_cv_.notify_all();
+}
+
+void BatchProcessor::monitor_directory(const std::string& input_dir, const std::string& output_dir) {
+  using namespace std::chrono;
+  const double idle_exit = Config::watch_idle_exit_sec();
+  auto last_activity = steady_clock::now();
+  for (int poll = 0; !stop_watch_; ++poll) {
+    if (poll % 15 == 0) std::printf("[INFO] [Watch] Monitoring directory: %s (Waiting for new files...)\n", input_dir.c_str());
+    std::error_code ec;
+    for (fs::directory_iterator it(input_dir, ec), end; !ec && it != end; it.increment(ec)) {
+      if (!it->is_regular_file(ec)) continue;
+      const std::string path = it->path().string();
+      std::string ext = it->path().extension().string();
+      for (char& ch : ext) ch = (char)std::tolower((unsigned char)ch);
+      if ((accept_ && !accept_(ext)) || seen_.count(path)) continue;
+      if (fs::exists(fs::path(output_dir) / it->path().filename())) {  // persistence across restarts (:262-269)
+        std::printf("[INFO] [Watch] Skipping file (already processed): %s\n", it->path().filename().c_str());
+        seen_.insert(path);
+        continue;
+      }
+      const auto size1 = fs::file_size(path, ec);  // still being written? (:273-279)
+      std::this_thread::sleep_for(milliseconds(500));
+      const auto size2 = fs::file_size(path, ec);
+      if (ec || size1 != size2) continue;
+      std::printf("[INFO] [Watch] New file detected: %s\n", it->path().filename().c_str());
+      {
+        std::lock_guard<std::mutex> lk(queue_mu_);
+        work_.push(path);
+        seen_.insert(path);
+      }
+      queue_cv_.notify_one();
+      last_activity = steady_clock::now();
+    }
+    bool busy;
+    {
+      std::lock_guard<std::mutex> lk(queue_mu_);
+      busy = !work_.empty() || in_progress_.load() > 0;
+    }
+    if (busy) last_activity = steady_clock::now();
+    else if (idle_exit > 0 && duration<double>(steady_clock::now() - last_activity).count() >= idle_exit) stop_watch();
+    for (int k = 0; k < 20 && !stop_watch_; ++k) std::this_thread::sleep_for(milliseconds(100));  // 2 s poll (:297)
+  }
+  queue_cv_.notify_all();
 }
 
 void BatchProcessor::stream_worker(int stream_id, int gpu, const std::string& output_dir) {
@@ -48,14 +100,18 @@ void BatchProcessor::stream_worker(int stream_id, int gpu, const std::string& ou
     r.frames = p.frames_scanned();
     r.n_segments = p.get_segments().size();
     if (r.rc != 0) failures_++;
-    std::lock_guard<std::mutex> lk(results_mu_);
-    results_.push_back(std::move(r));
+    {
+      std::lock_guard<std::mutex> lk(results_mu_);
+      results_.push_back(std::move(r));
+    }
+    in_progress_--;
   }
 }
 
 int BatchProcessor::process(const std::vector<std::string>& input_files, const std::string& output_dir,
-                            const std::string&) {
-  if (input_files.empty()) {
+                            const std::string& input_dir_arg) {
+  watching_ = Config::watch_mode();
+  if (input_files.empty() && !watching_) {
     std::printf("[WARN] No input files to process\n");
     return 0;
   }
@@ -63,9 +119,11 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
     const std::string out = (fs::path(output_dir) / fs::path(f).filename()).string();
     if (fs::exists(out)) {
       std::printf("[INFO] Skipping existing output: %s\n", out.c_str());
+      seen_.insert(f);
       continue;
     }
     work_.push(f);
+    seen_.insert(f);
   }
   if (!pool_.open(Config::gpus())) {
     std::printf("[ERROR] %s\n", pool_.error().c_str());
@@ -85,6 +143,14 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
   for (int g = 0; g < n_gpus; ++g)
     for (int s = 0; s < streams_per_gpu_; ++s)
       streams.emplace_back(&BatchProcessor::stream_worker, this, g * streams_per_gpu_ + s, g, output_dir);
+  if (watching_) {  // :161-183 — the monitor feeds the queue until stopped
+    std::string input_dir = input_dir_arg;
+    if (input_dir.empty() && !input_files.empty()) input_dir = fs::path(input_files[0]).parent_path().string();
+    if (input_dir.empty()) input_dir = ".";
+    std::printf("[INFO] Starting Watch Mode on directory: %s\n", input_dir.c_str());
+    std::thread monitor(&BatchProcessor::monitor_directory, this, input_dir, output_dir);
+    monitor.join();
+  }
   for (auto& t : streams) t.join();
   ffmpeg_queue_.finish();
   ffmpeg_worker.join();

@@ -48,6 +48,7 @@ int main(int argc, char** argv) {
     std::sort(files.begin(), files.end());
     if (!fs::exists(output)) fs::create_directories(output);
     BatchProcessor batch(Config::parallel_streams());
+    batch.set_input_filter(accepted);
     const int failed = batch.process(files, output, input);
     if (print_segments)
       for (const auto& r : batch.results())
@@ -56,12 +57,14 @@ int main(int argc, char** argv) {
     return failed > 0 ? 1 : 0;
   }
   GpuPool pool;
-  if (!pool.open(1)) {
+  if (!pool.open(std::max(1, Config::split_gpus()))) {
     std::printf("[ERROR] %s\n", pool.error().c_str());
     return 1;
   }
   ProcessingPipeline p(input, output, -1, Config::threads_per_stream());
-  p.set_gpu(&pool, 0);
+  std::vector<int> gpus;
+  for (int g = 0; g < pool.size(); ++g) gpus.push_back(g);  // > 1 only with MOTION_TRIM_SPLIT_GPUS
+  p.set_gpus(&pool, gpus);
   const int rc = p.run();
   if (print_segments) {
     std::printf("RESULT decision=%d duration=%a time_removed=%a saved_pct=%a segments=%zu\n", p.get_decision(), p.get_duration(),

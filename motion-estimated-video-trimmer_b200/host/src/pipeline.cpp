@@ -35,22 +35,28 @@ ProcessingPipeline::ProcessingPipeline(std::string in, std::string out, int stre
     : input_path_(std::move(in)), output_path_(std::move(out)), stream_id_(stream_id), num_threads_(num_threads),
       cpu_set_(std::move(cpu_set)) {}
 
-void ProcessingPipeline::set_gpu(GpuPool* pool, int gpu_index) {
+void ProcessingPipeline::set_gpu(GpuPool* pool, int gpu_index) { set_gpus(pool, {gpu_index}); }
+
+void ProcessingPipeline::set_gpus(GpuPool* pool, std::vector<int> gpu_indices) {
   pool_ = pool;
-  gpu_index_ = gpu_index;
+  gpus_ = std::move(gpu_indices);
+  gpu_index_ = gpus_.empty() ? -1 : gpus_.front();
 }
 
 int ProcessingPipeline::run() {
-  if (!pool_ || gpu_index_ < 0 || gpu_index_ >= pool_->size()) {
+  bool gpus_ok = pool_ && !gpus_.empty();
+  for (int g : gpus_) gpus_ok = gpus_ok && g >= 0 && g < pool_->size();
+  if (!gpus_ok) {
     logf(stream_id_, "[ERROR] ", "no GPU context (the motion scan has no CPU fallback)");
     return 1;
   }
   mscan_ctx* gpu = pool_->ctx(gpu_index_);
+  const size_t n_gpus = gpus_.size();
   if (!MemoryLoader::load_file(input_path_, file_buffer_)) {
     logf(stream_id_, "[ERROR] ", "Failed to map file: " + input_path_);
     return 1;
   }
-  const uint32_t video_id = pool_->next_video_id();
+  const uint32_t video_id = pool_->next_video_id();  // the same id on every GPU that scans this video
   double fps = 0;
   int width = 0, height = 0;
   bool decode_fed = false;
@@ -80,21 +86,34 @@ int ProcessingPipeline::run() {
   // (decode-fed runs stage projected records instead: nothing is DMA'd out of the media file)
   if (!decode_fed && !std::getenv("MOTION_TRIM_NO_PIN"))
     registered = mscan_host_register(gpu, const_cast<uint8_t*>(file_buffer_.data()), file_buffer_.size(), 1) == MSCAN_OK;
+  std::vector<mscan_ctx*> readers;  // every context that may DMA out of the mapping
+  for (int g : gpus_) readers.push_back(pool_->ctx(g));
   struct Unpin {
-    mscan_ctx* g;
+    std::vector<mscan_ctx*> gs;
     const uint8_t* p;
     bool on;
     ~Unpin() {
       if (!on) return;
-      mscan_host_fence(g);  // no DMA may still be reading the mapping
-      mscan_host_unregister(g, const_cast<uint8_t*>(p));
+      for (mscan_ctx* g : gs) mscan_host_fence(g);  // no DMA may still be reading the mapping
+      mscan_host_unregister(gs.front(), const_cast<uint8_t*>(p));
     }
-  } unpin{gpu, file_buffer_.data(), registered};
-  if (mscan_video_open(gpu, video_id, width, height) != MSCAN_OK) {
-    logf(stream_id_, "[ERROR] ", std::string("mscan_video_open: ") + mscan_last_error(gpu));
-    return 1;
+  } unpin{readers, file_buffer_.data(), registered};
+  for (size_t k = 0; k < n_gpus; ++k) {
+    mscan_ctx* g = pool_->ctx(gpus_[k]);
+    if (mscan_video_open(g, video_id, width, height) != MSCAN_OK) {
+      logf(stream_id_, "[ERROR] ", std::string("mscan_video_open: ") + mscan_last_error(g));
+      for (size_t j = 0; j < k; ++j) mscan_video_close(pool_->ctx(gpus_[j]), video_id);
+      return 1;
+    }
   }
+  auto close_all = [&] {
+    for (int g : gpus_) mscan_video_close(pool_->ctx(g), video_id);
+  };
   char buf[160];
+  if (n_gpus > 1) {
+    std::snprintf(buf, sizeof buf, "Splitting the video over %zu GPUs (stitched on GPU %d)", n_gpus, gpu_index_);
+    logf(stream_id_, "[INFO] ", buf);
+  }
   std::snprintf(buf, sizeof buf, "Duration: %.2fs (%.0f frames @ %.1ffps) on GPU %d%s", duration_, duration_ * fps, fps, gpu_index_,
                 decode_fed ? ", FFmpeg export_mvs front-end" : registered ? ", input pinned for in-place DMA" : "");
   logf(stream_id_, "[INFO] ", buf);
@@ -106,13 +125,14 @@ int ProcessingPipeline::run() {
   for (double t = 0; t < duration_; t += chunk) tasks.push_back(ScanTask{t, std::min(t + chunk, duration_), id++});
   int n_threads = num_threads_ > 0 ? num_threads_ : std::max(2u, std::thread::hardware_concurrency());
   n_threads = std::max(1, std::min<int>(n_threads, (int)tasks.size()));
+  n_threads = std::max<int>(n_threads, (int)std::min(n_gpus, tasks.size()));  // every GPU gets a worker
   std::atomic<size_t> next{0};
   std::atomic<long> frames{0};
   std::atomic<bool> failed{false};
   std::vector<std::thread> workers;
   for (int w = 0; w < n_threads; ++w)
-    workers.emplace_back([&] {
-      MotionScanner scanner(file_buffer_, gpu, video_id);
+    workers.emplace_back([&, w] {
+      MotionScanner scanner(file_buffer_, pool_->ctx(gpus_[(size_t)w % n_gpus]), video_id);
       if (!scanner.initialize()) {
         failed = true;
         return;
@@ -131,9 +151,16 @@ int ProcessingPipeline::run() {
   frames_scanned_ = (uint64_t)frames.load();
   if (failed) {
     logf(stream_id_, "[ERROR] ", std::string("scan failed: ") + mscan_last_error(gpu));
-    mscan_video_close(gpu, video_id);
+    close_all();
     return 1;
   }
+  // ---- cross-GPU stitch: the other GPUs' per-frame results join the first GPU's log (NVLink peer copy)
+  for (size_t k = 1; k < n_gpus; ++k)
+    if (mscan_video_append_from(gpu, video_id, pool_->ctx(gpus_[k]), video_id) != MSCAN_OK) {
+      logf(stream_id_, "[ERROR] ", std::string("mscan_video_append_from: ") + mscan_last_error(gpu));
+      close_all();
+      return 1;
+    }
 
   // ---- merge + segments + savings + decision on the GPU (pipeline.cpp:297-358)
   segments_.assign(64, TimeSegment{0, 0});
@@ -146,7 +173,7 @@ int ProcessingPipeline::run() {
     rc = mscan_segments(gpu, video_id, duration_, reinterpret_cast<mscan_segment*>(segments_.data()),
                         (uint32_t)segments_.size(), &n_seg, &res);
   }
-  mscan_video_close(gpu, video_id);
+  close_all();
   if (rc != MSCAN_OK) {
     logf(stream_id_, "[ERROR] ", std::string("mscan_segments: ") + mscan_last_error(gpu));
     return 1;

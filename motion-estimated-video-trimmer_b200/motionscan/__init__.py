@@ -79,6 +79,7 @@ class Stats(C.Structure):
         ("segment_ms", C.c_double),
         ("records_projected", C.c_uint64),
         ("project_ms", C.c_double),
+        ("peer_bytes", C.c_uint64),
     ]
 
 
@@ -150,6 +151,7 @@ SYMBOLS = {
     "mscan_motion_segments": (_i, [_vp, _u32, _d, _vp, _u32, _P(_u32), _P(VideoResult)]),
     "mscan_segments_batch": (_i, [_vp, _u32, _vp, _vp, _vp, _u64, _vp, _vp]),
     "mscan_video_close": (_i, [_vp, _u32]),
+    "mscan_video_append_from": (_i, [_vp, _u32, _vp, _u32]),
     "mscan_host_alloc": (_i, [_vp, C.c_size_t, _P(_vp)]),
     "mscan_host_free": (_i, [_vp, _vp]),
     "mscan_host_register": (_i, [_vp, _vp, C.c_size_t, _i]),
@@ -381,6 +383,10 @@ class Context:
             return self.segments_batch(vids, durations, int(off[n]))
         self._ck(rc)
         return out[: int(off[n])].copy(), off, res
+
+    def video_append_from(self, vid: int, src: "Context", src_vid: int):
+        """Cross-GPU stitch: this context's video `vid` adopts the frame results of (src, src_vid)."""
+        self._ck(self.L.mscan_video_append_from(self.h, vid, src.h, src_vid))
 
     def video_close(self, vid: int):
         self._ck(self.L.mscan_video_close(self.h, vid))

@@ -33,7 +33,7 @@ def test_struct_layouts():
     assert C.sizeof(ms.Params) == 56
     assert C.sizeof(ms.Geometry) == 16
     assert C.sizeof(ms.VideoResult) == 40 and ms.RESULT_DTYPE.itemsize == 40
-    assert C.sizeof(ms.Stats) == 88
+    assert C.sizeof(ms.Stats) == 96
     assert ms.MV8_DTYPE.itemsize == 8
     assert C.sizeof(ms.MvgenSpec) == 88
 
