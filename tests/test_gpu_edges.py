@@ -146,7 +146,16 @@ def test_fullsize_properties_device_resident():
         ctx.d2h(f3, d_f)
         ctx.d2h(c3, d_c)
         assert np.array_equal(f3, outs[0][0]) and np.array_equal(c3, outs[0][1])
-        for d in (d_cnt, d_off, d_recs, d_pts, d_f, d_c):
+        # layout invariance: the 8-byte projection of the stream (device-side) scans to the same log
+        d_r8 = ctx.dev_alloc(8 * n_rec + 256)
+        ctx.pack_records_device(d_recs, n_rec, d_r8)
+        ctx.scan_device_packed(d_r8, d_off, None, [geom], n, d_f, d_c)
+        ctx.sync()
+        f8, c8 = np.zeros(n, np.uint8), np.zeros(n, np.uint32)
+        ctx.d2h(f8, d_f)
+        ctx.d2h(c8, d_c)
+        assert np.array_equal(f8, outs[0][0]) and np.array_equal(c8, outs[0][1])
+        for d in (d_cnt, d_off, d_recs, d_pts, d_f, d_c, d_r8):
             ctx.dev_free(d)
     flags, counts = outs[0]
     assert 0 < flags.sum() < n and counts.max() > 10

@@ -6,6 +6,7 @@
 // Build: nvcc -O3 -std=c++17 -arch=sm_100a -Xcompiler -O3,-march=native,-pthread tools/exp_hostfeed.cu -o gpurun_out/exp_hostfeed
 #include <cuda_runtime.h>
 #include <immintrin.h>
+#include <sys/mman.h>
 
 #include <atomic>
 #include <chrono>
@@ -189,6 +190,49 @@ int main() {
                 best_of(pack_stream_pf<2048, _MM_HINT_T0>), best_of(pack_stream_pf<4096, _MM_HINT_T0>),
                 best_of(pack_stream_pf<1024, _MM_HINT_NTA>), best_of(pack_stream_pf<2048, _MM_HINT_T1>),
                 best_of(pack_stream_2way), best_of(pack_stream_4way));
+  }
+  // (c3) longer prefetch distances, and a transparent-huge-page backed pinned source
+  {
+    const int T = hw;
+    auto best_of = [&](const uint8_t* src, auto fn) {
+      double t = 1e9;
+      for (int rep = 0; rep < 3; ++rep) t = std::min(t, run_threads(T, n, [&](uint64_t a, uint64_t b) { fn(src + 40 * a, b - a, h_pk + a); }));
+      return n / t / 1e9;
+    };
+    std::printf("(c3) %d threads, cudaHostAlloc source: pf4096 %.2f | pf8192 %.2f | pf16384 %.2f | pf32768 %.2f G rec/s\n", T,
+                best_of(h_nat, pack_stream_pf<4096, _MM_HINT_T0>), best_of(h_nat, pack_stream_pf<8192, _MM_HINT_T0>),
+                best_of(h_nat, pack_stream_pf<16384, _MM_HINT_T0>), best_of(h_nat, pack_stream_pf<32768, _MM_HINT_T0>));
+    const size_t bytes = n * 40;
+    void* m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (m != MAP_FAILED) {
+      const int adv = madvise(m, bytes, MADV_HUGEPAGE);
+      uint8_t* hp = static_cast<uint8_t*>(m);
+      run_threads(T, n, [&](uint64_t a, uint64_t b) { std::memcpy(hp + 40 * a, h_nat + 40 * a, 40 * (b - a)); });
+      const cudaError_t reg = cudaHostRegister(hp, bytes, cudaHostRegisterPortable);
+      std::printf("(c3) THP source: madvise=%d cudaHostRegister=%s\n", adv, cudaGetErrorString(reg));
+      std::printf("(c3) %d threads, THP source: base %.2f | pf4096 %.2f | pf16384 %.2f G rec/s\n", T, best_of(hp, pack_stream),
+                  best_of(hp, pack_stream_pf<4096, _MM_HINT_T0>), best_of(hp, pack_stream_pf<16384, _MM_HINT_T0>));
+      if (reg == cudaSuccess) {
+        double bb = 0;
+        for (int i = 0; i < 4; ++i) {
+          CK(cudaEventRecord(e0, st));
+          CK(cudaMemcpyAsync(d, hp, 1ull << 30, cudaMemcpyHostToDevice, st));
+          CK(cudaEventRecord(e1, st));
+          CK(cudaStreamSynchronize(st));
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          bb = std::max(bb, (double)(1ull << 30) / ms / 1e6);
+        }
+        std::printf("(c3) H2D from the THP-backed registered buffer: %.1f GB/s\n", bb);
+        cudaHostUnregister(hp);
+      }
+      FILE* f = std::fopen("/sys/kernel/mm/transparent_hugepage/enabled", "r");
+      if (f) {
+        char line[128] = {0};
+        if (std::fgets(line, sizeof line, f)) std::printf("(c3) THP setting: %s", line);
+        std::fclose(f);
+      }
+      munmap(m, bytes);
+    }
   }
   // (c') projection overlapped with the DMA of the previous chunk (what the staging ring does)
   {
