@@ -616,7 +616,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-records", type=float, default=3e7, help="records of the CPU-baseline / reference-arm sample")
     ap.add_argument("--cpu-frames", type=int, default=0, help="override: frames of the CPU sample")
-    ap.add_argument("--slab-mb", type=int, default=256)
+    ap.add_argument("--slab-mb", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true", help="skip the device-resident K-A<packed> measurement")
     args = ap.parse_args()

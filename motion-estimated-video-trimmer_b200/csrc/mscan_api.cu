@@ -275,6 +275,17 @@ struct mscan_ctx {
   int pack_threads = 0;  // 0 → default_pack_threads() at first use
   std::unique_ptr<PackPool> pool;
 
+  // MSCAN_TRACE=1: wall time per ABI entry point (including time spent waiting for the context mutex),
+  // printed to stderr by mscan_destroy — the role of the reference's TIMER_START/END + TimingCollector
+  // (include/motion_trim/logging.hpp:137-148) for the calls that replaced its analyze phase.
+  struct ApiTime {
+    uint64_t calls = 0;
+    double total_ms = 0, max_ms = 0;
+  };
+  bool trace = false;
+  std::mutex trace_mu;
+  std::map<std::string, ApiTime> api_times;
+
   mscan_stats stats{};
   bool profiling = false;
   std::vector<EvPair> ev_pending;
@@ -282,6 +293,24 @@ struct mscan_ctx {
 };
 
 namespace {
+
+struct ApiTimer {
+  mscan_ctx* c;
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  ApiTimer(mscan_ctx* ctx, const char* n) : c(ctx && ctx->trace ? ctx : nullptr), name(n) {
+    if (c) t0 = std::chrono::steady_clock::now();
+  }
+  ~ApiTimer() {
+    if (!c) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lk(c->trace_mu);
+    auto& t = c->api_times[name];
+    t.calls += 1;
+    t.total_ms += ms;
+    t.max_ms = std::max(t.max_ms, ms);
+  }
+};
 
 int fail(mscan_ctx* c, int code, const char* fmt, ...) {
   if (c) {
@@ -685,12 +714,13 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   if (!c) return MSCAN_ERR_NOMEM;
   c->device = device;
   c->params = *p;
+  if (const char* t = std::getenv("MSCAN_TRACE")) c->trace = t[0] && t[0] != '0';
   threshold_to_int(p->mv_threshold_sq, &c->ithr, &c->keep_none);
   c->vec_need = (uint32_t)(uint8_t)p->vectors_needed;  // config.hpp:75 static_cast<uint8_t>
   c->clust_need = p->clusters_needed < 1 ? 1u : (uint32_t)p->clusters_needed;
   c->adj8 = p->adjacency == 8 ? 1u : 0u;
   c->log_cap = max_log_frames ? max_log_frames : (16ull << 20);
-  c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (256ull << 20);
+  c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (64ull << 20);
   c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
 
   auto bail = [&](int code) {
@@ -736,6 +766,16 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
 
 int mscan_destroy(mscan_ctx* c) {
   if (!c) return MSCAN_OK;
+  if (c->trace && !c->api_times.empty()) {
+    std::fprintf(stderr, "[mscan trace] device %d: wall time per entry point (lock waits included)\n", c->device);
+    for (const auto& kv : c->api_times)
+      std::fprintf(stderr, "[mscan trace]   %-28s calls %8llu  total %10.3f ms  max %9.3f ms\n", kv.first.c_str(),
+                   (unsigned long long)kv.second.calls, kv.second.total_ms, kv.second.max_ms);
+    std::fprintf(stderr, "[mscan trace]   projected %llu records in %.3f ms; H2D %llu B, D2H %llu B; K-A launches %llu, K-C launches %llu\n",
+                 (unsigned long long)c->stats.records_projected, c->stats.project_ms, (unsigned long long)c->stats.h2d_bytes,
+                 (unsigned long long)c->stats.d2h_bytes, (unsigned long long)c->stats.scan_launches,
+                 (unsigned long long)c->stats.segment_launches);
+  }
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& p : c->ev_pending) {
@@ -789,6 +829,7 @@ int mscan_get_params(mscan_ctx* c, mscan_params* p) {
 }
 
 int mscan_sync(mscan_ctx* c) {
+  ApiTimer trace_(c, "mscan_sync");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -825,6 +866,7 @@ int mscan_set_profiling(mscan_ctx* c, int enabled) {
 
 // ---- host-fed path ------------------------------------------------------------------------------
 int mscan_video_open_geometry(mscan_ctx* c, uint32_t video_id, const mscan_geometry* g) {
+  ApiTimer trace_(c, "mscan_video_open");
   if (!c || !g) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -860,6 +902,7 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
 // Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
 static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
                        const void* recs, bool src_packed, uint64_t* first_frame_out) {
+  ApiTimer trace_(c, "mscan_submit[_packed]");
   if (!c) return MSCAN_ERR_INVALID;
   if (n_frames == 0) {
     if (first_frame_out) {
@@ -1026,6 +1069,7 @@ int mscan_set_pack_threads(mscan_ctx* c, int n_threads) {
 }
 
 int mscan_flush(mscan_ctx* c) {
+  ApiTimer trace_(c, "mscan_flush");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -1033,6 +1077,7 @@ int mscan_flush(mscan_ctx* c) {
 }
 
 int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) {
+  ApiTimer trace_(c, "mscan_collect");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -1055,6 +1100,7 @@ int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* cou
 }
 
 int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags, uint32_t* counts) {
+  ApiTimer trace_(c, "mscan_collect_range");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -1181,6 +1227,7 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
 static int segments_impl(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
                          mscan_segment* out, uint64_t cap, uint64_t* seg_off_out, mscan_video_result* res_out,
                          bool job_semantics) {
+  ApiTimer trace_(c, "mscan_segments[_batch]");
   if (!c || (n_videos && (!ids || !durations))) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
@@ -1239,6 +1286,7 @@ int mscan_motion_segments(mscan_ctx* c, uint32_t video_id, double duration, msca
 }
 
 int mscan_video_close(mscan_ctx* c, uint32_t video_id) {
+  ApiTimer trace_(c, "mscan_video_close");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   auto it = c->videos.find(video_id);
@@ -1326,6 +1374,7 @@ int mscan_host_free(mscan_ctx* c, void* p) {
 }
 
 int mscan_host_register(mscan_ctx* c, void* p, size_t bytes, int read_only) {
+  ApiTimer trace_(c, "mscan_host_register");
   if (!c || !p || !bytes) return MSCAN_ERR_INVALID;
   CU(cudaSetDevice(c->device));
   unsigned flags = cudaHostRegisterPortable;
@@ -1347,6 +1396,7 @@ int mscan_host_unregister(mscan_ctx* c, void* p) {
 }
 
 int mscan_host_fence(mscan_ctx* c) {
+  ApiTimer trace_(c, "mscan_host_fence");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));

@@ -27,6 +27,7 @@ struct StreamResult {
   double seconds = 0, duration = 0, time_removed = 0, saved_pct = 0;
   uint64_t frames = 0, records = 0;
   size_t n_segments = 0;
+  double t_map = 0, t_probe = 0, t_pin = 0, t_scan = 0, t_segments = 0, t_unpin = 0;
 };
 
 class BatchProcessor {

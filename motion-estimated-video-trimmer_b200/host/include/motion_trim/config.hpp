@@ -60,6 +60,8 @@ MT_KNOB(int, threads_per_stream, detail::env_i32("THREADS_PER_STREAM", 0))  // c
 MT_KNOB(bool, watch_mode, detail::env_i32("WATCH_MODE", 0) != 0)
 // new: how many GPUs of the box to use (0 = all)
 MT_KNOB(int, gpus, detail::env_i32("MOTION_TRIM_GPUS", 0))
+// new: size of each of the library's three record slabs (+ pinned staging), MiB (0 = library default)
+MT_KNOB(int, slab_mb, detail::env_i32("MOTION_TRIM_SLAB_MB", 0))
 // new: single-file mode only — split the one video over this many GPUs (0/1 = one GPU); SURVEY §8(f) N4
 MT_KNOB(int, split_gpus, detail::env_i32("MOTION_TRIM_SPLIT_GPUS", 0))
 // new: watch mode ends after this many idle seconds (0 = never, like the reference)

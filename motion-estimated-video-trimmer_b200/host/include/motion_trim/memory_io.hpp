@@ -25,6 +25,7 @@ class MappedFile {
   const uint8_t* data() const { return data_; }
   size_t size() const { return size_; }
   bool is_valid() const { return data_ != nullptr; }
+  void will_need() const;  // asynchronous read-ahead of the whole mapping (decode-fed inputs)
 
  private:
   friend class MemoryLoader;
@@ -36,7 +37,7 @@ class MappedFile {
 
 class MemoryLoader {
  public:
-  // mmap(PROT_READ, MAP_PRIVATE|MAP_POPULATE) + madvise, like the reference (src/memory_io.cpp:103-115)
+  // mmap(PROT_READ, MAP_PRIVATE) + madvise(SEQUENTIAL); the reference's MAP_POPULATE (src/memory_io.cpp:103-115) only with MOTION_TRIM_POPULATE=1
   static bool load_file(const std::string& path, MappedFile& file);
 };
 

@@ -36,6 +36,11 @@ class ProcessingPipeline {
   int get_decision() const { return decision_; }
   const std::vector<TimeSegment>& get_segments() const { return segments_; }
   uint64_t frames_scanned() const { return frames_scanned_; }
+  // wall seconds per phase of run() (the reference's TIMER_START/END records, src/pipeline.cpp:95-292)
+  struct Phases {
+    double map = 0, probe = 0, pin = 0, scan = 0, segments = 0, unpin = 0;
+  };
+  const Phases& phases() const { return phases_; }
   uint64_t records_scanned() const { return records_scanned_; }
 
  private:
@@ -45,6 +50,7 @@ class ProcessingPipeline {
   int decision_ = MSCAN_NO_MOTION;
   std::vector<TimeSegment> segments_;
   uint64_t frames_scanned_ = 0, records_scanned_ = 0;
+  Phases phases_;
   int stream_id_;
   int num_threads_;
   std::vector<int> cpu_set_;

@@ -99,6 +99,11 @@ void BatchProcessor::stream_worker(int stream_id, int gpu, const std::string& ou
     r.saved_pct = p.get_saved_pct();
     r.frames = p.frames_scanned();
     r.n_segments = p.get_segments().size();
+    r.t_map = p.phases().map;
+    r.t_probe = p.phases().probe;
+    r.t_pin = p.phases().pin;
+    r.t_scan = p.phases().scan;
+    r.t_segments = p.phases().segments;
     if (r.rc != 0) failures_++;
     {
       std::lock_guard<std::mutex> lk(results_mu_);
@@ -156,15 +161,22 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
   ffmpeg_worker.join();
 
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  double sum = 0;
+  double sum = 0, ph[5] = {0, 0, 0, 0, 0};
   uint64_t frames = 0;
   for (const auto& r : results_) {
     sum += r.seconds;
     frames += r.frames;
+    ph[0] += r.t_map;
+    ph[1] += r.t_probe;
+    ph[2] += r.t_pin;
+    ph[3] += r.t_scan;
+    ph[4] += r.t_segments;
   }
   std::printf("========== BATCH SUMMARY ==========\n");
   std::printf("files %zu  failed %d  frames %llu  wall %.3fs  speedup %.2fx (sum of file times / wall)\n", results_.size(),
               failures_.load() + mux_failures.load(), (unsigned long long)frames, wall, wall > 0 ? sum / wall : 0.0);
+  std::printf("phases (sum over files, s): map %.3f  probe %.3f  pin %.3f  submit %.3f  segments+close %.3f  other %.3f\n", ph[0], ph[1],
+              ph[2], ph[3], ph[4], sum - ph[0] - ph[1] - ph[2] - ph[3] - ph[4]);
   return failures_.load() + mux_failures.load();
 }
 

@@ -1,6 +1,10 @@
 // gpu_pool.cpp — libmotionscan contexts, one per GPU.
 #include "motion_trim/gpu_pool.hpp"
 
+#include <algorithm>
+
+#include "motion_trim/config.hpp"
+
 namespace motion_trim {
 
 GpuPool::~GpuPool() {
@@ -22,7 +26,7 @@ bool GpuPool::open(int max_gpus) {
   if (max_gpus > 0 && max_gpus < n) n = max_gpus;
   for (int g = 0; g < n; ++g) {
     mscan_ctx* c = nullptr;
-    rc = mscan_create(g, &params_, 0, 0, &c);
+    rc = mscan_create(g, &params_, 0, (uint64_t)std::max(0, Config::slab_mb()) << 20, &c);
     if (rc != MSCAN_OK) {
       error_ = std::string("mscan_create failed: ") + mscan_status_string(rc);
       return false;

@@ -52,10 +52,17 @@ int ProcessingPipeline::run() {
   }
   mscan_ctx* gpu = pool_->ctx(gpu_index_);
   const size_t n_gpus = gpus_.size();
+  using clk = std::chrono::steady_clock;
+  auto lap = [t = clk::now()](double& into) mutable {
+    const auto n = clk::now();
+    into += std::chrono::duration<double>(n - t).count();
+    t = n;
+  };
   if (!MemoryLoader::load_file(input_path_, file_buffer_)) {
     logf(stream_id_, "[ERROR] ", "Failed to map file: " + input_path_);
     return 1;
   }
+  lap(phases_.map);
   const uint32_t video_id = pool_->next_video_id();  // the same id on every GPU that scans this video
   double fps = 0;
   int width = 0, height = 0;
@@ -76,28 +83,34 @@ int ProcessingPipeline::run() {
     height = probe.height();
     decode_fed = probe.uses_ffmpeg();
   }
+  if (decode_fed) file_buffer_.will_need();
   if (!(duration_ > 0)) {  // the reference divides by zero here (pipeline.cpp:141-143,259); refuse instead
     logf(stream_id_, "[ERROR] ", "stream has no duration");
     return 1;
   }
+  lap(phases_.probe);
   // Pin the mapped stream so mscan_submit DMAs records straight out of the page cache; if the platform
   // refuses (or MOTION_TRIM_NO_PIN is set) submits fall back to the library's pinned staging copy.
   bool registered = false;
   // (decode-fed runs stage projected records instead: nothing is DMA'd out of the media file)
   if (!decode_fed && !std::getenv("MOTION_TRIM_NO_PIN"))
     registered = mscan_host_register(gpu, const_cast<uint8_t*>(file_buffer_.data()), file_buffer_.size(), 1) == MSCAN_OK;
+  lap(phases_.pin);
   std::vector<mscan_ctx*> readers;  // every context that may DMA out of the mapping
   for (int g : gpus_) readers.push_back(pool_->ctx(g));
   struct Unpin {
     std::vector<mscan_ctx*> gs;
     const uint8_t* p;
     bool on;
+    double* seconds;
     ~Unpin() {
       if (!on) return;
+      const auto t0 = clk::now();
       for (mscan_ctx* g : gs) mscan_host_fence(g);  // no DMA may still be reading the mapping
       mscan_host_unregister(gs.front(), const_cast<uint8_t*>(p));
+      *seconds += std::chrono::duration<double>(clk::now() - t0).count();
     }
-  } unpin{readers, file_buffer_.data(), registered};
+  } unpin{readers, file_buffer_.data(), registered, &phases_.unpin};
   for (size_t k = 0; k < n_gpus; ++k) {
     mscan_ctx* g = pool_->ctx(gpus_[k]);
     if (mscan_video_open(g, video_id, width, height) != MSCAN_OK) {
@@ -148,6 +161,7 @@ int ProcessingPipeline::run() {
       }
     });
   for (auto& t : workers) t.join();
+  lap(phases_.scan);
   frames_scanned_ = (uint64_t)frames.load();
   if (failed) {
     logf(stream_id_, "[ERROR] ", std::string("scan failed: ") + mscan_last_error(gpu));
@@ -174,6 +188,7 @@ int ProcessingPipeline::run() {
                         (uint32_t)segments_.size(), &n_seg, &res);
   }
   close_all();
+  lap(phases_.segments);
   if (rc != MSCAN_OK) {
     logf(stream_id_, "[ERROR] ", std::string("mscan_segments: ") + mscan_last_error(gpu));
     return 1;

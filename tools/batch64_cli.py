@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3] through the product CLI: a batch of 64 synthetic 60 s 1080p30 clips (MVS1 files,
+seeds 100..163) handed to `motion_trim_b200 <dir> <out>`, whose BatchProcessor deals the files to
+PARALLEL_STREAMS stream threads per GPU (batch_processor.cpp role) — the videos are sharded over the GPUs,
+nothing is exchanged between them. Reports wall time and records/s for 1, 2, 4, 8 GPUs (those the box has)
+(the mapped records are projected by the library's staging pass: cudaHostRegister refuses tmpfs/page-cache
+mappings on this platform, so the in-place DMA of mapped files does not apply), with the mapping lazy (default)
+or populated up front like the reference's.
+
+    python tools/batch64_cli.py [--clips 64] [--frames 1800] [--dir /dev/shm/mscan_batch64]
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT / "motion-estimated-video-trimmer_b200"), str(ROOT / "tests")]
+import motionscan as ms  # noqa: E402
+import mvs_io  # noqa: E402
+
+BIN = ROOT / "motion-estimated-video-trimmer_b200" / "host" / "motion_trim_b200"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--clips", type=int, default=64)
+    ap.add_argument("--frames", type=int, default=1800)
+    ap.add_argument("--dir", default="/dev/shm/mscan_batch64")
+    ap.add_argument("--gpus", default="1,2,4,8")
+    ap.add_argument("--streams", type=int, default=2, help="PARALLEL_STREAMS per GPU (shipped env: 2)")
+    ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--modes", default="default,populate")
+    args = ap.parse_args()
+    import ctypes as C
+
+    n_dev = C.c_int()
+    ms.lib().mscan_device_count(C.byref(n_dev))
+    ind, threads = Path(args.dir) / "in", os.cpu_count() or 8
+    ind.mkdir(parents=True, exist_ok=True)
+    t0, n_rec, expect = time.time(), 0, {}
+    for k in range(args.clips):
+        spec = ms.synth_preset(3, 100 + k)
+        cnt, off, recs, pts = ms.synth_host(spec, 0, args.frames, n_threads=threads)
+        mvs_io.write_mvs(ind / f"clip{k:03d}.mvs", spec.width, spec.height, int(spec.fps), 1, np.arange(args.frames), cnt, recs)
+        n_rec += int(off[-1])
+    print(f"# generated {args.clips} clips x {args.frames} frames = {n_rec} records ({n_rec * 40 / 1e9:.1f} GB) in {time.time() - t0:.1f} s", flush=True)
+    env0 = dict(os.environ, MV_THRESHOLD_SQ="4.0", VECTORS_NEEDED="4", CLUSTERS_NEEDED="2", VERTICAL_MASK="0.05", MAX_GAP_SEC="5",
+                PADDING_SEC="0.5", MIN_SAVINGS_PCT="5", CHUNK_DURATION_SEC="60", TARGET_FPS="0", THREADS_PER_STREAM="1",
+                PARALLEL_STREAMS=str(args.streams))
+    baseline = None
+    for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)]:
+        for mode, extra in (("default", {}), ("populate", {"MOTION_TRIM_POPULATE": "1"})):
+            if mode not in args.modes.split(","):
+                continue
+            outd = Path(args.dir) / f"out_{g}_{mode}"
+            shutil.rmtree(outd, ignore_errors=True)
+            t = time.time()
+            r = subprocess.run([str(BIN), "--print-segments", str(ind), str(outd)], env=dict(env0, MOTION_TRIM_GPUS=str(g), **extra),
+                               capture_output=True, text=True)
+            wall = time.time() - t
+            m = re.search(r"wall ([0-9.]+)s", r.stdout)
+            scan_wall = float(m.group(1)) if m else float("nan")
+            res = {ln.split()[1]: ln.split()[2:] for ln in r.stdout.splitlines() if ln.startswith("RESULT ")}
+            dec = {k: [x for x in v if x.startswith("decision=") or x.startswith("saved_pct=")] for k, v in sorted(res.items())}
+            if baseline is None:
+                baseline = dec
+            ph = re.search(r"phases \(sum over files, s\): (.*)", r.stdout)
+            print(json.dumps({"gpus": g, "feed": mode, "phases": ph.group(1) if ph else None, "streams_per_gpu": args.streams, "rc": r.returncode, "files": len(res),
+                              "batch_wall_s": scan_wall, "process_wall_s": round(wall, 3), "records_per_s": n_rec / scan_wall,
+                              "same_results_as_first_run": dec == baseline}), flush=True)
+    if not args.keep:
+        shutil.rmtree(args.dir, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
