@@ -2,6 +2,7 @@
 #include "motion_trim/gpu_pool.hpp"
 
 #include <algorithm>
+#include <thread>
 
 #include "motion_trim/config.hpp"
 
@@ -33,6 +34,10 @@ bool GpuPool::open(int max_gpus) {
     }
     ctx_.push_back(c);
   }
+  // the contexts' projection pools share the host: cores / GPUs threads each (a pool per context sized for the
+  // whole box would oversubscribe it n-fold)
+  const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
+  for (mscan_ctx* c : ctx_) mscan_set_pack_threads(c, (int)std::max(1u, cores / (unsigned)ctx_.size()));
   return true;
 }
 
