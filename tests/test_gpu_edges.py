@@ -198,3 +198,47 @@ def test_host_register_and_fence_allow_buffer_reuse():
         assert np.array_equal(c, oc) and np.array_equal(f, of)
     assert f1.any() and f2.any() and not np.array_equal(c1, c2)
     assert st.h2d_bytes >= 40 * (len(a[2]) + len(b[2]))
+
+
+@pytest.mark.parametrize("scrambled", [False, True])
+def test_kc_ten_hour_video(scrambled):
+    """K-C at its largest realistic size: a 10-hour 30 fps video (1 080 000 frames), in order and with its
+    900-frame chunks delivered in random order plus duplicated chunks (sort + unique over 2^21 slots);
+    segments, savings and decision bit-exact with the oracle's restatement of pipeline.cpp:302-404."""
+    n, fps = 1_080_000, 30.0
+    rng = np.random.default_rng(11)
+    pts = np.arange(n, dtype=np.float64) / fps
+    flags = np.zeros(n, np.uint8)
+    for a in rng.integers(0, n - 3000, 400):  # 400 motion events of 1..100 s
+        flags[a : a + int(rng.integers(30, 3000))] = 1
+    flags &= (rng.random(n) < 0.9).astype(np.uint8)  # flicker inside events
+    if scrambled:
+        order = rng.permutation(n // 900)
+        order = np.concatenate([order, order[:25]])  # some chunks arrive twice
+        idx = (order[:, None] * 900 + np.arange(900)[None, :]).reshape(-1)
+        pts, flags = pts[idx], flags[idx]
+    p = kats.env_params()
+    duration = n / fps
+    osegs, ores = orc.video_tail(pts, flags, duration, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+    m = len(pts)
+    with ms.Context(0, p) as ctx:
+        d_pts, d_flags = ctx.dev_alloc(8 * m), ctx.dev_alloc(m)
+        d_segs, d_res = ctx.dev_alloc(16 * m), ctx.dev_alloc(40)
+        ctx.h2d(d_pts, pts)
+        ctx.h2d(d_flags, flags)
+        ctx.set_profiling(True)
+        for _ in range(2):
+            ctx.segments_device([0, m], [duration], d_pts, d_flags, d_segs, d_res)
+        ctx.sync()
+        st = ctx.stats()
+        res = np.zeros(1, ms.RESULT_DTYPE)
+        ctx.d2h(res, d_res)
+        segs = np.zeros(int(res["n_segments"][0]), ms.SEG_DTYPE)
+        ctx.d2h(segs, d_segs)
+        for d in (d_pts, d_flags, d_segs, d_res):
+            ctx.dev_free(d)
+    assert int(res["decision"][0]) == ores.decision and int(res["n_motion_frames"][0]) == ores.n_motion_frames
+    assert segs.tobytes() == osegs.tobytes() and len(segs) > 100
+    assert np.float64(res["saved_pct"][0]).tobytes() == np.float64(ores.saved_pct).tobytes()
+    print(f"K-C {m} frames scrambled={scrambled}: {st.segment_ms / st.segment_launches:.3f} ms per launch")
+    assert st.segment_ms / st.segment_launches < 2000.0
