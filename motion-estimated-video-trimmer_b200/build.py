@@ -16,7 +16,7 @@ ROOT = HERE.parent
 CSRC = HERE / "csrc"
 OUT = HERE / "libmotionscan.so"
 
-SOURCES = ["ka_scan.cu", "kc_segments.cu", "synth.cu", "synth_host.cu", "mscan_api.cu"]
+SOURCES = ["ka_scan.cu", "ka_scan_cluster.cu", "kc_segments.cu", "synth.cu", "synth_host.cu", "mscan_api.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "kernels.cuh", ROOT / "include" / "motionscan.h", ROOT / "include" / "mvgen_core.h"]
 
 NVCC_FLAGS = [

@@ -404,6 +404,44 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
   return false;
 }
 
+bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, bool packed, ScanPlan* plan) {
+  uint32_t cells = 0, words = 0;
+  for (uint32_t i = 0; i < n_geoms; ++i) {
+    cells = max(cells, (uint32_t)geoms[i].gw * (uint32_t)geoms[i].gh);
+    words = max(words, (uint32_t)geoms[i].gh * (((uint32_t)geoms[i].gw + 31u) >> 5));
+  }
+  const bool ok = scan_plan(cells, words, smem_optin, packed, plan);
+  plan->cluster = 0;
+  plan->cells = cells;
+  plan->bit_words = words;
+  if (ok && !plan->global_cnt) return true;
+  if (env_u32("MSCAN_KA_NO_CLUSTER")) return ok;
+  // the grid does not fit one CTA: distribute it over a cluster's shared memory in row bands (ka_scan_cluster.cu)
+  for (uint32_t C = 2; C <= 8; C *= 2) {
+    uint32_t band_cells = 0, band_words = 0;
+    for (uint32_t i = 0; i < n_geoms; ++i) {
+      const uint32_t rpr = ((uint32_t)geoms[i].gh + C - 1) / C;
+      band_cells = max(band_cells, rpr * (uint32_t)geoms[i].gw);
+      band_words = max(band_words, rpr * (((uint32_t)geoms[i].gw + 31u) >> 5));
+    }
+    for (uint32_t st = 4; st >= 2; --st) {
+      const uint32_t need = scan_cluster_smem(st, band_cells, band_words);
+      if (need > smem_optin) continue;
+      plan->stages = st;
+      plan->smem_bytes = need;
+      plan->ctas_per_sm = 1;
+      plan->global_cnt = 0;
+      plan->cons_warps = 16;
+      plan->cnt16 = 1;
+      plan->cluster = C;
+      plan->cells = band_cells;
+      plan->bit_words = band_words;
+      return true;
+    }
+  }
+  return ok;
+}
+
 namespace {
 template <bool kPacked>
 cudaError_t configure_all(int v) {
@@ -437,6 +475,7 @@ void launch_one(const ScanArgs& a, const ScanPlan& plan, uint32_t grid, cudaStre
 cudaError_t scan_configure(uint32_t smem_optin) {
   cudaError_t e = configure_all<false>((int)smem_optin);
   if (e == cudaSuccess) e = configure_all<true>((int)smem_optin);
+  if (e == cudaSuccess) e = scan_cluster_configure(smem_optin);
   return e;
 }
 
@@ -447,6 +486,7 @@ uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames) {
 
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
+  if (plan.cluster) return scan_cluster_launch(a, plan, num_sms, st);
   const uint32_t grid = scan_grid(plan, num_sms, a.n_frames);
   if (a.packed) launch_one<true>(a, plan, grid, st);
   else launch_one<false>(a, plan, grid, st);

@@ -47,11 +47,20 @@ struct ScanPlan {
   uint32_t global_cnt;  // counters do not fit shared memory: use the global scratch
   uint32_t cons_warps;  // 8 (two CTAs per SM) or 16 (one CTA per SM)
   uint32_t cnt16;       // 16-bit shared-memory counters (half the footprint, guarded against carry)
+  uint32_t cluster;     // 0, or the cluster size (2/4/8) of ka_scan_cluster.cu: the grid lives in DSMEM row bands
+  uint32_t cells;       // → ScanArgs.max_cells (whole grid, or one band under a cluster plan)
+  uint32_t bit_words;   // → ScanArgs.max_bit_words
 };
 
 // Chooses ring depth / occupancy for the largest geometry and the record layout; false if it cannot fit.
 bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, bool packed, ScanPlan* plan);
+// The plan for a set of geometries: single-CTA if the largest grid fits shared memory, else a cluster plan
+// (grid distributed over 2/4/8 CTAs), else the global-counter fallback. Fills plan->cells / bit_words.
+bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, bool packed, ScanPlan* plan);
 cudaError_t scan_configure(uint32_t smem_optin);
+uint32_t scan_cluster_smem(uint32_t stages, uint32_t band_cells, uint32_t band_bit_words);
+cudaError_t scan_cluster_configure(uint32_t smem_optin);
+cudaError_t scan_cluster_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st);
 uint32_t scan_grid(const ScanPlan& plan, int num_sms, uint32_t n_frames);
 cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st);
 

@@ -33,6 +33,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -124,8 +125,12 @@ constexpr uint64_t kPoolMinRecs = 1 << 18;  // smaller jobs are projected by the
 // hold the context mutex).
 class PackPool {
  public:
-  explicit PackPool(int workers) {
-    for (int i = 0; i < workers; ++i) th_.emplace_back([this] { worker(); });
+  // Starts up to `workers` threads; if the platform refuses some, the pool simply runs with fewer.
+  explicit PackPool(int workers) noexcept {
+    try {
+      for (int i = 0; i < workers; ++i) th_.emplace_back([this] { worker(); });
+    } catch (...) {
+    }
   }
   ~PackPool() {
     {
@@ -324,6 +329,19 @@ int fail(mscan_ctx* c, int code, const char* fmt, ...) {
   return code;
 }
 
+// No exception crosses the ABI: every entry point that can allocate is a function-try-block ending here.
+int on_exception(mscan_ctx* c) noexcept {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    return c ? fail(c, MSCAN_ERR_NOMEM, "out of host memory") : MSCAN_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    return c ? fail(c, MSCAN_ERR_INVALID, "internal error: %s", e.what()) : MSCAN_ERR_INVALID;
+  } catch (...) {
+    return c ? fail(c, MSCAN_ERR_INVALID, "internal error") : MSCAN_ERR_INVALID;
+  }
+}
+
 #define CU(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
@@ -468,8 +486,8 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   a.n_frames = n;
   const ScanPlan& plan = s.packed ? c->plan_packed : c->plan;
   a.stages = plan.stages;
-  a.max_cells = c->max_cells;
-  a.max_bit_words = c->max_bit_words;
+  a.max_cells = plan.cells;
+  a.max_bit_words = plan.bit_words;
   int rc = run_scan(c, a, plan, s.stream, s.seg_recs);
   if (rc) return rc;
   CU(cudaEventRecord(s.done, s.stream));
@@ -522,10 +540,10 @@ int sync_scans_locked(mscan_ctx* c) {
   return MSCAN_OK;
 }
 
-int replan(mscan_ctx* c) {
+int replan(mscan_ctx* c, const std::vector<DevGeom>& geoms) {
   ScanPlan p, pp;
-  if (!scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, false, &p) ||
-      !scan_plan(c->max_cells, c->max_bit_words, c->smem_optin, true, &pp))
+  if (!scan_plan_for(geoms.data(), (uint32_t)geoms.size(), c->smem_optin, false, &p) ||
+      !scan_plan_for(geoms.data(), (uint32_t)geoms.size(), c->smem_optin, true, &pp))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells: bit-rows do not fit shared memory", c->max_cells);
   if (p.global_cnt && (uint64_t)c->num_sms * p.ctas_per_sm * c->max_cells * sizeof(uint32_t) > (16ull << 30))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells needs more than 16 GiB of counter scratch", c->max_cells);
@@ -551,7 +569,9 @@ int add_geometry(mscan_ctx* c, const mscan_geometry& g, uint32_t* idx) {
   c->max_cells = std::max(c->max_cells, cells);
   c->max_bit_words = std::max(c->max_bit_words, words);
   if (c->max_cells != old_cells || c->max_bit_words != old_words) {
-    int rc = replan(c);
+    std::vector<DevGeom> all(c->geoms);
+    all.push_back(d);
+    int rc = replan(c, all);
     if (rc) {
       c->max_cells = old_cells;
       c->max_bit_words = old_words;
@@ -828,7 +848,7 @@ int mscan_get_params(mscan_ctx* c, mscan_params* p) {
   return MSCAN_OK;
 }
 
-int mscan_sync(mscan_ctx* c) {
+int mscan_sync(mscan_ctx* c) try {
   ApiTimer trace_(c, "mscan_sync");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -837,24 +857,30 @@ int mscan_sync(mscan_ctx* c) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
-int mscan_get_stats(mscan_ctx* c, mscan_stats* s) {
+int mscan_get_stats(mscan_ctx* c, mscan_stats* s) try {
   if (!c || !s) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
   drain_events(c);
   *s = c->stats;
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
-int mscan_reset_stats(mscan_ctx* c) {
+int mscan_reset_stats(mscan_ctx* c) try {
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
   drain_events(c);
   c->stats = mscan_stats{};
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_set_profiling(mscan_ctx* c, int enabled) {
@@ -865,7 +891,7 @@ int mscan_set_profiling(mscan_ctx* c, int enabled) {
 }
 
 // ---- host-fed path ------------------------------------------------------------------------------
-int mscan_video_open_geometry(mscan_ctx* c, uint32_t video_id, const mscan_geometry* g) {
+int mscan_video_open_geometry(mscan_ctx* c, uint32_t video_id, const mscan_geometry* g) try {
   ApiTimer trace_(c, "mscan_video_open");
   if (!c || !g) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -889,6 +915,8 @@ int mscan_video_open_geometry(mscan_ctx* c, uint32_t video_id, const mscan_geome
   v.geom = idx;
   c->videos.emplace(video_id, std::move(v));
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
@@ -901,7 +929,7 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
 
 // Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
 static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                       const void* recs, bool src_packed, uint64_t* first_frame_out) {
+                       const void* recs, bool src_packed, uint64_t* first_frame_out) try {
   ApiTimer trace_(c, "mscan_submit[_packed]");
   if (!c) return MSCAN_ERR_INVALID;
   if (n_frames == 0) {
@@ -990,9 +1018,9 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
           if (take_recs >= kPoolMinRecs) {
             if (!c->pool) {
               const int nthr = c->pack_threads > 0 ? c->pack_threads : default_pack_threads();
-              c->pool.reset(new PackPool(nthr - 1));
+              c->pool.reset(new (std::nothrow) PackPool(nthr - 1));
             }
-            if (c->pool->workers() > 0) c->pool->run(from, to, take_recs);
+            if (c->pool && c->pool->workers() > 0) c->pool->run(from, to, take_recs);
             else project_records(from, take_recs, to);
           } else {
             project_records(from, take_recs, to);
@@ -1031,6 +1059,8 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     }
   }
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
@@ -1060,23 +1090,27 @@ int mscan_set_staging_mode(mscan_ctx* c, int mode) {
   return MSCAN_OK;
 }
 
-int mscan_set_pack_threads(mscan_ctx* c, int n_threads) {
+int mscan_set_pack_threads(mscan_ctx* c, int n_threads) try {
   if (!c || n_threads < 0) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   c->pack_threads = n_threads;
   c->pool.reset();  // re-created with the new size at the next large projection
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
-int mscan_flush(mscan_ctx* c) {
+int mscan_flush(mscan_ctx* c) try {
   ApiTimer trace_(c, "mscan_flush");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   return flush_locked(c);
+} catch (...) {
+  return on_exception(c);
 }
 
-int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) {
+int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) try {
   ApiTimer trace_(c, "mscan_collect");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1097,9 +1131,11 @@ int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* cou
   }
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
-int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags, uint32_t* counts) {
+int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags, uint32_t* counts) try {
   ApiTimer trace_(c, "mscan_collect_range");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1125,6 +1161,8 @@ int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_
   }
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 // Runs K-C for a list of open videos; leaves results in c->h_res and segments on the device.
@@ -1226,7 +1264,7 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
 
 static int segments_impl(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
                          mscan_segment* out, uint64_t cap, uint64_t* seg_off_out, mscan_video_result* res_out,
-                         bool job_semantics) {
+                         bool job_semantics) try {
   ApiTimer trace_(c, "mscan_segments[_batch]");
   if (!c || (n_videos && (!ids || !durations))) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1262,6 +1300,8 @@ static int segments_impl(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, c
   CU(cudaStreamSynchronize(c->main_stream));
   if (overflow) return fail(c, MSCAN_ERR_CAPACITY, "segment buffer too small: need %llu", (unsigned long long)at);
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_segments_batch(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
@@ -1285,7 +1325,7 @@ int mscan_motion_segments(mscan_ctx* c, uint32_t video_id, double duration, msca
   return rc;
 }
 
-int mscan_video_close(mscan_ctx* c, uint32_t video_id) {
+int mscan_video_close(mscan_ctx* c, uint32_t video_id) try {
   ApiTimer trace_(c, "mscan_video_close");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1300,12 +1340,14 @@ int mscan_video_close(mscan_ctx* c, uint32_t video_id) {
     c->log_head = 0;
   }
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 // Cross-GPU stitch: the frames another context scanned for the same video join this
 // context's log by a peer copy of their 13 B/frame (NVLink when the GPUs are peers), so that K-C sees the
 // whole video. The union/sort/unique of chunk results (pipeline.cpp:268,302-304) then happens in K-C as usual.
-int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, uint32_t src_video) {
+int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, uint32_t src_video) try {
   if (!dst || !src) return MSCAN_ERR_INVALID;
   mscan_ctx* c = dst;  // errors are reported on the destination context
   if (dst == src && dst_video == src_video) return fail(c, MSCAN_ERR_INVALID, "cannot append a video to itself");
@@ -1355,6 +1397,8 @@ int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, 
   dv.n_frames += sv.n_frames;
   dst->log_head += sv.n_frames;
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(dst);
 }
 
 int mscan_host_alloc(mscan_ctx* c, size_t bytes, void** p) {
@@ -1395,7 +1439,7 @@ int mscan_host_unregister(mscan_ctx* c, void* p) {
   return MSCAN_OK;
 }
 
-int mscan_host_fence(mscan_ctx* c) {
+int mscan_host_fence(mscan_ctx* c) try {
   ApiTimer trace_(c, "mscan_host_fence");
   if (!c) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1405,6 +1449,8 @@ int mscan_host_fence(mscan_ctx* c) {
   for (auto& s : c->slabs)
     if (s.in_flight) CU(cudaEventSynchronize(s.copied));
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 // ---- device-resident path -----------------------------------------------------------------------
@@ -1451,7 +1497,7 @@ int mscan_offsets_from_counts(mscan_ctx* c, const uint32_t* d_cnt, uint32_t n, u
 
 static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const uint64_t* d_rec_off,
                             const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms, uint32_t n_frames,
-                            uint8_t* d_flags, uint32_t* d_counts, void* stream) {
+                            uint8_t* d_flags, uint32_t* d_counts, void* stream) try {
   if (!c || !d_rec_off || !geoms || n_geoms == 0 || !d_flags || !d_counts) return MSCAN_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(d_recs) & 15u) != 0) return fail(c, MSCAN_ERR_INVALID, "d_recs must be 16-byte aligned");
   if (n_geoms > kMaxGeoms) return fail(c, MSCAN_ERR_CAPACITY, "too many geometries");
@@ -1469,7 +1515,7 @@ static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const
     words = std::max(words, wo);
   }
   ScanPlan plan;
-  if (!scan_plan(cells, words, c->smem_optin, packed, &plan))
+  if (!scan_plan_for(dg.data(), n_geoms, c->smem_optin, packed, &plan))
     return fail(c, MSCAN_ERR_UNSUPPORTED, "block grid of %u cells does not fit shared memory", cells);
   if (n_geoms > c->user_geoms_cap) {
     cudaFree(c->d_user_geoms);
@@ -1495,9 +1541,11 @@ static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const
   a.counts = d_counts;
   a.n_frames = n_frames;
   a.stages = plan.stages;
-  a.max_cells = cells;
-  a.max_bit_words = words;
+  a.max_cells = plan.cells;
+  a.max_bit_words = plan.bit_words;
   return run_scan(c, a, plan, st, 0);
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_scan_device(mscan_ctx* c, const mscan_mv* d_recs, const uint64_t* d_rec_off, const uint32_t* d_frame_geom,
@@ -1525,7 +1573,7 @@ int mscan_pack_records_device(mscan_ctx* c, const mscan_mv* d_recs, uint64_t n, 
 
 int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_video_off, const double* h_durations,
                           const double* d_pts, const uint8_t* d_flags, mscan_segment* d_segments,
-                          mscan_video_result* d_results, void* stream) {
+                          mscan_video_result* d_results, void* stream) try {
   if (!c || !h_video_off || !h_durations || !d_pts || !d_flags || !d_segments || !d_results) return MSCAN_ERR_INVALID;
   if (n_videos == 0) return MSCAN_OK;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -1615,6 +1663,8 @@ int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_vid
   }
   c->stats.segment_launches += 1;
   return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 // ---- measurement harness ------------------------------------------------------------------------
