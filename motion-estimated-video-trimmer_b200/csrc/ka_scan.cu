@@ -416,28 +416,42 @@ bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, 
   plan->bit_words = words;
   if (ok && !plan->global_cnt) return true;
   if (env_u32("MSCAN_KA_NO_CLUSTER")) return ok;
-  // the grid does not fit one CTA: distribute it over a cluster's shared memory in row bands (ka_scan_cluster.cu)
+  // The grid does not fit one CTA: distribute it over a cluster's shared memory in row bands (ka_scan_cluster.cu).
+  // Ring depth decides the streaming rate (≥ 7 stages ≈ 140 KB in flight per SM, as for grids that fit), so the
+  // cluster size is the smallest one whose bands leave room for 7 stages, else the one with the deepest ring
+  // (8K: 2 CTAs → 4 stages 6.8 TB/s, 4 CTAs → 8 stages 7.2 TB/s; profiles/r02_ka_cluster_sweep.log).
+  const uint32_t want_c = env_u32("MSCAN_KA_CLUSTER"), want_stages = env_u32("MSCAN_KA_CLUSTER_STAGES");  // experiments
+  uint32_t best_c = 0, best_st = 0, best_cells = 0, best_words = 0;
   for (uint32_t C = 2; C <= 8; C *= 2) {
+    if (want_c && C != want_c) continue;
     uint32_t band_cells = 0, band_words = 0;
     for (uint32_t i = 0; i < n_geoms; ++i) {
       const uint32_t rpr = ((uint32_t)geoms[i].gh + C - 1) / C;
       band_cells = max(band_cells, rpr * (uint32_t)geoms[i].gw);
       band_words = max(band_words, rpr * (((uint32_t)geoms[i].gw + 31u) >> 5));
     }
-    for (uint32_t st = 4; st >= 2; --st) {
-      const uint32_t need = scan_cluster_smem(st, band_cells, band_words);
-      if (need > smem_optin) continue;
-      plan->stages = st;
-      plan->smem_bytes = need;
-      plan->ctas_per_sm = 1;
-      plan->global_cnt = 0;
-      plan->cons_warps = 16;
-      plan->cnt16 = 1;
-      plan->cluster = C;
-      plan->cells = band_cells;
-      plan->bit_words = band_words;
-      return true;
+    uint32_t st = want_stages ? want_stages : 8;
+    while (st >= 2 && scan_cluster_smem(st, band_cells, band_words) > smem_optin) --st;
+    if (st < 2) continue;
+    if (st > best_st) {
+      best_c = C;
+      best_st = st;
+      best_cells = band_cells;
+      best_words = band_words;
     }
+    if (st >= (packed ? 3u : 7u)) break;  // projected records are issue-bound, not HBM-bound: the smallest cluster wins
+  }
+  if (best_c) {
+    plan->stages = best_st;
+    plan->smem_bytes = scan_cluster_smem(best_st, best_cells, best_words);
+    plan->ctas_per_sm = 1;
+    plan->global_cnt = 0;
+    plan->cons_warps = 16;
+    plan->cnt16 = 1;
+    plan->cluster = best_c;
+    plan->cells = best_cells;
+    plan->bit_words = best_words;
+    return true;
   }
   return ok;
 }
