@@ -97,3 +97,39 @@ def test_pack_records_is_the_byte_range_6_to_14():
     # misaligned output is refused, not silently mis-stored
     buf = np.zeros(8 * 4 + 4, np.uint8)
     assert ms.lib().mscan_pack_records(recs.ctypes.data, 4, buf.ctypes.data + 4) == ms.ERR_INVALID
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/motionscan.h compiles as C99 (-pedantic) and a C program links against libmotionscan.so: the ABI
+    really is plain C (no C++ types, no torch types). The program only calls GPU-free entry points."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "motionscan.h"
+int main(void) {
+  mscan_params p;
+  mscan_geometry g;
+  mscan_mv recs[3];
+  mscan_mv8 out[3];
+  int i;
+  if (mscan_abi_version() != MSCAN_ABI_VERSION) return 1;
+  if (mscan_params_default(&p) != MSCAN_OK) return 2;
+  if (mscan_geometry_from_dims(&p, 1920, 1080, &g) != MSCAN_OK || g.grid_w != 120 || g.grid_h != 68 || g.vertical_margin != 3) return 3;
+  memset(recs, 0, sizeof recs);
+  for (i = 0; i < 3; ++i) { recs[i].src_x = (int16_t)(10 + i); recs[i].src_y = -7; recs[i].dst_x = (int16_t)(100 * i); recs[i].dst_y = 32767; }
+  if (mscan_pack_records(recs, 3, out) != MSCAN_OK) return 4;
+  for (i = 0; i < 3; ++i) if (out[i].src_x != 10 + i || out[i].src_y != -7 || out[i].dst_x != 100 * i || out[i].dst_y != 32767) return 5;
+  printf("%d %d %s\n", (int)sizeof(mscan_mv), (int)sizeof(mscan_mv8), mscan_status_string(MSCAN_ERR_CUDA));
+  return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    pkg = ROOT / "motion-estimated-video-trimmer_b200"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                    "-L", str(pkg), "-lmotionscan", f"-Wl,-rpath,{pkg}"], check=True, capture_output=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split()[:2] == ["40", "8"]
