@@ -16,6 +16,7 @@
 
 #include "ffmpeg_queue.hpp"
 #include "gpu_pool.hpp"
+#include "memory_io.hpp"
 
 namespace motion_trim {
 
@@ -58,6 +59,12 @@ class BatchProcessor {
   std::function<bool(const std::string&)> accept_;
   std::atomic<bool> watching_{false}, stop_watch_{false};
   std::atomic<int> in_progress_{0};
+  // finished inputs are unmapped off the stream threads
+  void reaper_loop();
+  std::mutex reap_mu_;
+  std::condition_variable reap_cv_;
+  std::queue<MappedFile> reap_;
+  bool reap_done_ = false;
   std::vector<StreamResult> results_;
   std::atomic<int> failures_{0};
 };

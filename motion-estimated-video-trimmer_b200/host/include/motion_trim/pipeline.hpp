@@ -41,6 +41,9 @@ class ProcessingPipeline {
     double map = 0, probe = 0, pin = 0, scan = 0, segments = 0, unpin = 0;
   };
   const Phases& phases() const { return phases_; }
+  // Hands the input mapping to the caller (the batch processor unmaps finished inputs on a side thread:
+  // tearing down a 720 MB mapping costs ≈ 9 ms, more than projecting its records).
+  MappedFile release_input() { return std::move(file_buffer_); }
   uint64_t records_scanned() const { return records_scanned_; }
 
  private:

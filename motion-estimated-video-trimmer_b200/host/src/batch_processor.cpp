@@ -30,6 +30,19 @@ bool BatchProcessor::next_file(std::string& out) {
   return true;
 }
 
+void BatchProcessor::reaper_loop() {
+  for (;;) {
+    MappedFile f;
+    {
+      std::unique_lock<std::mutex> lk(reap_mu_);
+      reap_cv_.wait(lk, [this] { return !reap_.empty() || reap_done_; });
+      if (reap_.empty()) return;
+      f = std::move(reap_.front());
+      reap_.pop();
+    }
+  }  // ~MappedFile unmaps here, outside the lock
+}
+
 void BatchProcessor::stop_watch() {
   stop_watch_ = true;
   queue_cv_.notify_all();
@@ -104,6 +117,11 @@ void BatchProcessor::stream_worker(int stream_id, int gpu, const std::string& ou
     r.t_pin = p.phases().pin;
     r.t_scan = p.phases().scan;
     r.t_segments = p.phases().segments;
+    {
+      std::lock_guard<std::mutex> lk(reap_mu_);
+      reap_.push(p.release_input());
+    }
+    reap_cv_.notify_one();
     if (r.rc != 0) failures_++;
     {
       std::lock_guard<std::mutex> lk(results_mu_);
@@ -144,6 +162,7 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
     while (ffmpeg_queue_.pop(job))
       if (execute_ffmpeg_cut(job.input_path, job.output_path, job.segments, job.cpu_set, job.stream_id) != 0) mux_failures++;
   });
+  std::thread reaper(&BatchProcessor::reaper_loop, this);
   std::vector<std::thread> streams;
   for (int g = 0; g < n_gpus; ++g)
     for (int s = 0; s < streams_per_gpu_; ++s)
@@ -157,6 +176,13 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
     monitor.join();
   }
   for (auto& t : streams) t.join();
+  const double scan_wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  {
+    std::lock_guard<std::mutex> lk(reap_mu_);
+    reap_done_ = true;
+  }
+  reap_cv_.notify_all();
+  reaper.join();
   ffmpeg_queue_.finish();
   ffmpeg_worker.join();
 
@@ -173,8 +199,8 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
     ph[4] += r.t_segments;
   }
   std::printf("========== BATCH SUMMARY ==========\n");
-  std::printf("files %zu  failed %d  frames %llu  wall %.3fs  speedup %.2fx (sum of file times / wall)\n", results_.size(),
-              failures_.load() + mux_failures.load(), (unsigned long long)frames, wall, wall > 0 ? sum / wall : 0.0);
+  std::printf("files %zu  failed %d  frames %llu  wall %.3fs  (scan %.3fs)  speedup %.2fx (sum of file times / wall)\n", results_.size(),
+              failures_.load() + mux_failures.load(), (unsigned long long)frames, wall, scan_wall, wall > 0 ? sum / wall : 0.0);
   std::printf("phases (sum over files, s): map %.3f  probe %.3f  pin %.3f  submit %.3f  segments+close %.3f  other %.3f\n", ph[0], ph[1],
               ph[2], ph[3], ph[4], sum - ph[0] - ph[1] - ph[2] - ph[3] - ph[4]);
   return failures_.load() + mux_failures.load();
