@@ -422,7 +422,7 @@ bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, 
   // (8K: 2 CTAs → 4 stages 6.8 TB/s, 4 CTAs → 8 stages 7.2 TB/s; profiles/r02_ka_cluster_sweep.log).
   const uint32_t want_c = env_u32("MSCAN_KA_CLUSTER"), want_stages = env_u32("MSCAN_KA_CLUSTER_STAGES");  // experiments
   uint32_t best_c = 0, best_st = 0, best_cells = 0, best_words = 0;
-  for (uint32_t C = 2; C <= 8; C *= 2) {
+  for (uint32_t C = 2; C <= 16; C *= 2) {  // 16 is a non-portable cluster size (opt-in, B200 supports it)
     if (want_c && C != want_c) continue;
     uint32_t band_cells = 0, band_words = 0;
     for (uint32_t i = 0; i < n_geoms; ++i) {

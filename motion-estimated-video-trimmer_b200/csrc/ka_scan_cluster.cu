@@ -334,6 +334,9 @@ uint32_t scan_cluster_smem(uint32_t stages, uint32_t band_cells, uint32_t band_b
 cudaError_t scan_cluster_configure(uint32_t smem_optin) {
   cudaError_t e = cudaFuncSetAttribute(ka_scan_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+  // clusters of 16 CTAs (16K grids with a deep ring) are beyond the portable size of 8
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_cluster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(ka_scan_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   return e;
 }
 

@@ -63,13 +63,13 @@ def test_random_frames_big_grids(shape, mode):
 
 @pytest.mark.parametrize("shape", ["8k", "16k"])
 def test_clusters_across_band_boundaries(shape):
-    """Vertical pairs whose two cells belong to different CTAs of the cluster (every band boundary for 2, 4 and 8
+    """Vertical pairs whose two cells belong to different CTAs of the cluster (every band boundary for 2, 4, 8 and 16
     CTAs), horizontal pairs on the boundary rows, and a diagonal pair across a boundary (not a cluster)."""
     w, h = SHAPES[shape]
     p = kats.env_params()
     cfg, gw, gh, m = cfg_for(p, w, h)
     frames, want = [], []
-    for C in (2, 4, 8):
+    for C in (2, 4, 8, 16):
         rpr = -(-gh // C)
         for b in range(1, C):
             y = b * rpr  # first row of band b; y-1 is the last row of band b-1
