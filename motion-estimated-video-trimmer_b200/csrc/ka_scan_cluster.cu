@@ -1,5 +1,5 @@
 // ka_scan_cluster.cu — K-A for block grids that do not fit one CTA's shared memory (8K: 480x270 = 129 600
-// cells, 16K: 518 400): a thread-block cluster of 2/4/8 CTAs scans one frame together.
+// cells, 16K: 518 400): a thread-block cluster of 2/4/8/16 CTAs scans one frame together.
 //
 // Same computation as ka_scan.cu (check_frame, reference src/motion_scanner.cpp:217-295); what changes is
 // where the vote grid lives and who reads which records:
@@ -13,7 +13,7 @@
 //   * three cluster barriers per frame order votes → bit-rows → counts; frames are handed out by an atomic
 //     queue popped by CTA 0 and published to the cluster one frame ahead.
 // Before this kernel such grids used per-CTA counters in global memory (L2 atomics): 2.3 TB/s at 8K against
-// 7.5 TB/s for grids that fit (tools/ka_bigframe.py). That path remains for grids beyond 8 CTAs of shared memory.
+// 7.5 TB/s for grids that fit (tools/ka_bigframe.py). That path remains for grids beyond 16 CTAs of shared memory.
 #include "common.cuh"
 #include "kernels.cuh"
 
