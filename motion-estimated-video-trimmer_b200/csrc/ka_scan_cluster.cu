@@ -4,7 +4,9 @@
 // Same computation as ka_scan.cu (check_frame, reference src/motion_scanner.cpp:217-295); what changes is
 // where the vote grid lives and who reads which records:
 //   * the grid is distributed over the cluster's shared memory by row bands: CTA r owns rows
-//     [r*rpr, (r+1)*rpr), rpr = ceil(gh / C), as 16-bit counters (same carry guard as ka_scan.cu);
+//     [r*rpr, (r+1)*rpr), rpr = ceil(gh / C), as 16-bit counters with ka_scan.cu's carry guard: a warp adds at
+//     most 32 per trip, so at most 32 x 16 warps x 16 CTAs = 8 192 can slip past the 0x7FFF threshold, far from
+//     the 0x8000 that would carry into the word-mate;
 //   * the frame's records are cut into C contiguous slices, CTA r streams slice r through its own
 //     bulk-copy ring (HBM is read once); export_mvs order is raster order, so most votes of slice r land in
 //     band r — the rest go to the owning CTA with a DSMEM atomic (red.shared::cluster);
