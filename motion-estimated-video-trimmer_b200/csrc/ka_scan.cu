@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           const bool in = ((uint32_t)gx < (uint32_t)gw) && ((uint32_t)(gy - td.y_min) < live_rows);  // :262
           if (keep_any && mag >= ithr && in) key = gy * gw + gx;           // :251
         }
+        // nothing to vote in this warp trip (static macroblocks: the common CCTV case) — skip the merge
+        if (!__any_sync(0xffffffffu, key >= 0)) continue;
         // run-length merge of equal neighbouring keys inside the warp
         const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (lane == 0) || (key != prev);
