@@ -25,15 +25,23 @@ bool GpuPool::open(int max_gpus) {
     return false;
   }
   if (max_gpus > 0 && max_gpus < n) n = max_gpus;
+  // one creator thread per GPU: the first context on a device costs ≈ 0.5 s (primary context + module load),
+  // which would otherwise add up serially on an 8-GPU box
+  std::vector<mscan_ctx*> made((size_t)n, nullptr);
+  std::vector<int> rcs((size_t)n, MSCAN_OK);
+  std::vector<std::thread> creators;
+  const uint64_t slab_bytes = (uint64_t)std::max(0, Config::slab_mb()) << 20;
+  for (int g = 0; g < n; ++g)
+    creators.emplace_back([&, g] { rcs[(size_t)g] = mscan_create(g, &params_, 0, slab_bytes, &made[(size_t)g]); });
+  for (auto& t : creators) t.join();
   for (int g = 0; g < n; ++g) {
-    mscan_ctx* c = nullptr;
-    rc = mscan_create(g, &params_, 0, (uint64_t)std::max(0, Config::slab_mb()) << 20, &c);
-    if (rc != MSCAN_OK) {
-      error_ = std::string("mscan_create failed: ") + mscan_status_string(rc);
+    if (rcs[(size_t)g] != MSCAN_OK) {
+      error_ = std::string("mscan_create failed on GPU ") + std::to_string(g) + ": " + mscan_status_string(rcs[(size_t)g]);
+      for (mscan_ctx* c : made) mscan_destroy(c);
       return false;
     }
-    ctx_.push_back(c);
   }
+  ctx_ = made;
   // the contexts' projection pools share the host: cores / GPUs threads each (a pool per context sized for the
   // whole box would oversubscribe it n-fold)
   const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
