@@ -118,7 +118,7 @@ def test_cli_watch_mode_picks_up_new_files():
         import ref_runner
 
         env.update(ref_runner.env_for(p, 10.0, None))
-        env.update({"WATCH_MODE": "1", "MOTION_TRIM_WATCH_IDLE_EXIT_SEC": "4", "PARALLEL_STREAMS": "1"})
+        env.update({"WATCH_MODE": "1", "MOTION_TRIM_WATCH_IDLE_EXIT_SEC": "6", "PARALLEL_STREAMS": "1"})
         proc = subprocess.Popen([str(BIN), "--print-segments", str(ind), str(outd)], env=env, stdout=subprocess.PIPE,
                                 stderr=subprocess.STDOUT, text=True)
 
