@@ -45,7 +45,8 @@ using namespace mscan;
 namespace {
 
 constexpr int kSlabs = 3;
-constexpr int kWorkSlots = 16;
+constexpr int kWorkSlots = 16;  // frame queues: one per slab stream (launches on a stream are serialised) + a rotating
+                                 // pool for launches on caller streams (mscan_scan_device)
 constexpr uint32_t kMaxGeoms = 4096;
 
 struct Extent {
@@ -413,9 +414,12 @@ void drain_events(mscan_ctx* c) {
   c->ev_pending.clear();
 }
 
-int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaStream_t st, uint64_t n_recs) {
+int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaStream_t st, uint64_t n_recs, int slab_index = -1) {
   ScanArgs a = args_in;
-  a.work = c->d_work + 2 * (c->work_rr++ % kWorkSlots);
+  // two kernels must never share a frame queue while both run: a slab's launches are ordered by its stream, so
+  // the slab index is a safe slot; launches on caller streams rotate through the remaining slots
+  const uint32_t slot = slab_index >= 0 ? (uint32_t)slab_index : (uint32_t)kSlabs + (c->work_rr++ % (uint32_t)(kWorkSlots - kSlabs));
+  a.work = c->d_work + 2 * slot;
   a.adj8 = c->adj8;
   a.cnt_scratch = nullptr;
   if (plan.global_cnt) {
@@ -488,7 +492,7 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   a.stages = plan.stages;
   a.max_cells = plan.cells;
   a.max_bit_words = plan.bit_words;
-  int rc = run_scan(c, a, plan, s.stream, s.seg_recs);
+  int rc = run_scan(c, a, plan, s.stream, s.seg_recs, (int)(&s - c->slabs));
   if (rc) return rc;
   CU(cudaEventRecord(s.done, s.stream));
   s.in_flight = true;

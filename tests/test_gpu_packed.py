@@ -221,3 +221,32 @@ def test_scan_device_packed_matches_native():
     for f, c in out:
         assert np.array_equal(c, oc) and np.array_equal(f, of)
 
+
+
+def test_many_tiny_segments_across_the_slab_ring():
+    """300 single-frame submits that alternate record formats: every submit closes a segment (one K-A launch each),
+    slabs rotate many times, launches pile up on three streams — the log must still be the oracle's, in order."""
+    spec = ms.synth_preset(3, 55)
+    n = 300
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    p = kats.env_params()
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    with ms.Context(0, p, 0, 2 << 20) as ctx:  # 2 MiB slabs: a handful of frames each
+        hp = ctx.pinned_array(len(recs), ms.MV_DTYPE)
+        hp[:] = recs
+        r8 = ms.pack_records(recs)
+        ctx.video_open(1, spec.width, spec.height)
+        for i in range(n):
+            r0, r1 = int(off[i]), int(off[i + 1])
+            if i % 2:
+                ctx.submit(1, pts[i : i + 1], cnt[i : i + 1], hp[r0:r1])
+            else:
+                ctx.submit_packed(1, pts[i : i + 1], cnt[i : i + 1], r8[r0:r1])
+        flags, counts = ctx.collect(1)
+        segs, res = ctx.motion_segments(1, n / spec.fps)
+        st = ctx.stats()
+        ctx.host_free(hp.ctypes.data)
+    osegs, ores = orc.video_tail(pts, of, n / spec.fps, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+    assert np.array_equal(counts, oc) and np.array_equal(flags, of)
+    assert segs.tobytes() == osegs.tobytes() and res.decision == ores.decision
+    assert st.scan_launches >= 250  # I-frames carry no records and need no launch of their own
