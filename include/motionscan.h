@@ -162,7 +162,8 @@ int mscan_params_from_env(mscan_params* p);
 int mscan_geometry_from_dims(const mscan_params* p, int width, int height, mscan_geometry* g);
 
 /* ---- context (one per GPU; `submit` may be called from many threads) ---- */
-/* max_log_frames: capacity of the on-device frame log (0 → 16 Mi frames).
+/* max_log_frames: capacity of the on-device frame log (0 → 16 Mi frames) = the most frames that videos which are
+ * open at the same time can hold; frames of closed videos are reused.
  * slab_bytes: size of each of the 3 device record slabs + pinned staging (0 → 64 MiB: host-fed throughput is flat
  * from 32 to 256 MiB, profiles/r02_slab_sweep.log, while pinned staging costs ≈ 0.4 ms per MiB to allocate). */
 int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uint64_t slab_bytes,

@@ -241,6 +241,7 @@ struct mscan_ctx {
 
   // frame log
   uint64_t log_cap = 0, log_head = 0;
+  uint64_t log_limit = 0;  // frames [log_head, log_limit) are known to be free (space closed videos gave back is found on demand)
   double* d_pts = nullptr;
   uint8_t* d_flags = nullptr;
   uint32_t* d_counts = nullptr;
@@ -590,6 +591,40 @@ int add_geometry(mscan_ctx* c, const mscan_geometry& g, uint32_t* idx) {
   return MSCAN_OK;
 }
 
+// The frame log is reused: when the bump pointer runs out of known-free frames, the gaps between the extents of the
+// videos that are still open are searched first-fit, cyclically from the current head. Sets [log_head, log_limit) to
+// the gap found; false when every frame of the log belongs to an open video. The caller has closed the open
+// segment (its frames must be contiguous in the log) and frees nothing that a running kernel still writes:
+// mscan_video_close waits for the scans in flight.
+bool log_find_space(mscan_ctx* c) {
+  std::vector<Extent> live;
+  for (const auto& kv : c->videos)
+    for (const Extent& e : kv.second.extents)
+      if (e.n) live.push_back(e);
+  std::sort(live.begin(), live.end(), [](const Extent& x, const Extent& y) { return x.start < y.start; });
+  struct Gap {
+    uint64_t a, b;
+  };
+  std::vector<Gap> gaps;
+  uint64_t at = 0;
+  for (const Extent& e : live) {
+    if (e.start > at) gaps.push_back(Gap{at, e.start});
+    at = std::max(at, e.start + e.n);
+  }
+  if (at < c->log_cap) gaps.push_back(Gap{at, c->log_cap});
+  if (gaps.empty()) return false;
+  // first gap that ends after the current head (continue forward), else wrap to the first gap of the log
+  for (const Gap& g : gaps)
+    if (g.b > c->log_head) {
+      c->log_head = std::max(c->log_head, g.a);
+      c->log_limit = g.b;
+      return true;
+    }
+  c->log_head = gaps.front().a;
+  c->log_limit = gaps.front().b;
+  return true;
+}
+
 template <typename T>
 int grow(mscan_ctx* c, T** d, uint64_t* cap, uint64_t need) {
   if (need <= *cap) return MSCAN_OK;
@@ -744,6 +779,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   c->clust_need = p->clusters_needed < 1 ? 1u : (uint32_t)p->clusters_needed;
   c->adj8 = p->adjacency == 8 ? 1u : 0u;
   c->log_cap = max_log_frames ? max_log_frames : (16ull << 20);
+  c->log_limit = c->log_cap;
   c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (64ull << 20);
   c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
 
@@ -951,16 +987,6 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
   Video& v = it->second;
   if (first_frame_out) *first_frame_out = v.n_frames;
-  if (c->log_head + n_frames > c->log_cap) {
-    if (c->videos.size() == 1 && v.n_frames == 0 && n_frames <= c->log_cap) {
-      int rc = sync_scans_locked(c);
-      if (rc) return rc;
-      c->log_head = 0;  // nothing else lives in the log
-    } else {
-      return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames); close videos or create a larger context",
-                  (unsigned long long)c->log_cap);
-    }
-  }
   const uint8_t* src = reinterpret_cast<const uint8_t*>(recs);
   const bool pinned = recs && is_pinned(recs);
   // How the records reach the slab: native+pinned → DMA in place (40 B/record over PCIe, no host work);
@@ -985,10 +1011,18 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       int rc = launch_segment(c, *s);
       if (rc) return rc;
     }
-    // how many whole frames fit into the current slab
+    if (c->log_head >= c->log_limit) {  // out of known-free log frames: look for space closed videos gave back
+      int rc = launch_segment(c, *s);    // a segment's frames are contiguous in the log
+      if (rc) return rc;
+      if (!log_find_space(c))
+        return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos); close videos or create a larger context",
+                    (unsigned long long)c->log_cap);
+    }
+    // how many whole frames fit into the current slab (and into the free run of the log)
     uint32_t take = 0;
     uint64_t take_recs = 0;
-    while (f + take < n_frames && s->frames + take < c->slab_frames) {
+    const uint64_t log_room = c->log_limit - c->log_head;
+    while (f + take < n_frames && s->frames + take < c->slab_frames && take < log_room) {
       const uint64_t nb = (take_recs + rec_count[f + take]) * out_stride;
       if (s->bytes + nb > c->slab_bytes) break;
       if (take && take_recs + rec_count[f + take] > max_take_recs) break;
@@ -1335,13 +1369,14 @@ int mscan_video_close(mscan_ctx* c, uint32_t video_id) try {
   std::lock_guard<std::mutex> lk(c->mu);
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  // the video's log frames become reusable: no scan in flight may still write them
+  CU(cudaSetDevice(c->device));
+  int rc = sync_scans_locked(c);
+  if (rc) return rc;
   c->videos.erase(it);
-  if (c->videos.empty()) {
-    // the log holds nothing live any more: rewind it once in-flight scans are done
-    CU(cudaSetDevice(c->device));
-    int rc = sync_scans_locked(c);
-    if (rc) return rc;
+  if (c->videos.empty()) {  // nothing live any more: rewind
     c->log_head = 0;
+    c->log_limit = c->log_cap;
   }
   return MSCAN_OK;
 } catch (...) {
@@ -1365,8 +1400,6 @@ int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, 
   const Video& sv = sit->second;
   Video& dv = dit->second;
   if (sv.n_frames == 0) return MSCAN_OK;
-  if (dst->log_head + sv.n_frames > dst->log_cap)
-    return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames)", (unsigned long long)dst->log_cap);
   // the source's results must exist; the destination's open segment must not straddle the imported range
   if (cudaSetDevice(src->device) != cudaSuccess) return fail(c, MSCAN_ERR_CUDA, "cudaSetDevice(%d) failed", src->device);
   {
@@ -1387,19 +1420,29 @@ int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, 
     int rc = sync_scans_locked(dst);
     if (rc) return rc;
   }
-  uint64_t at = dst->log_head;
-  for (const Extent& e : sv.extents) {
-    CU(cudaMemcpyPeerAsync(dst->d_pts + at, dst->device, src->d_pts + e.start, src->device, sizeof(double) * e.n, dst->main_stream));
-    CU(cudaMemcpyPeerAsync(dst->d_flags + at, dst->device, src->d_flags + e.start, src->device, e.n, dst->main_stream));
-    CU(cudaMemcpyPeerAsync(dst->d_counts + at, dst->device, src->d_counts + e.start, src->device, sizeof(uint32_t) * e.n, dst->main_stream));
-    at += e.n;
+  const std::vector<Extent> src_extents = sv.extents;  // dst == src: dv.extents grows below
+  uint64_t done_frames = 0;
+  for (const Extent& e : src_extents) {
+    uint64_t off = 0;
+    while (off < e.n) {  // in pieces, as the free runs of the destination log allow
+      if (dst->log_head >= dst->log_limit && !log_find_space(dst)) {
+        CU(cudaStreamSynchronize(dst->main_stream));
+        return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos)", (unsigned long long)dst->log_cap);
+      }
+      const uint64_t m = std::min(e.n - off, dst->log_limit - dst->log_head), at = dst->log_head, from = e.start + off;
+      CU(cudaMemcpyPeerAsync(dst->d_pts + at, dst->device, src->d_pts + from, src->device, sizeof(double) * m, dst->main_stream));
+      CU(cudaMemcpyPeerAsync(dst->d_flags + at, dst->device, src->d_flags + from, src->device, m, dst->main_stream));
+      CU(cudaMemcpyPeerAsync(dst->d_counts + at, dst->device, src->d_counts + from, src->device, sizeof(uint32_t) * m, dst->main_stream));
+      if (!dv.extents.empty() && dv.extents.back().start + dv.extents.back().n == at) dv.extents.back().n += m;
+      else dv.extents.push_back(Extent{at, m});
+      dv.n_frames += m;
+      dst->log_head += m;
+      off += m;
+      done_frames += m;
+    }
   }
   CU(cudaStreamSynchronize(dst->main_stream));
-  dst->stats.peer_bytes += 13ull * sv.n_frames;
-  if (!dv.extents.empty() && dv.extents.back().start + dv.extents.back().n == dst->log_head) dv.extents.back().n += sv.n_frames;
-  else dv.extents.push_back(Extent{dst->log_head, sv.n_frames});
-  dv.n_frames += sv.n_frames;
-  dst->log_head += sv.n_frames;
+  dst->stats.peer_bytes += 13ull * done_frames;
   return MSCAN_OK;
 } catch (...) {
   return on_exception(dst);

@@ -242,3 +242,54 @@ def test_kc_ten_hour_video(scrambled):
     assert np.float64(res["saved_pct"][0]).tobytes() == np.float64(ores.saved_pct).tobytes()
     print(f"K-C {m} frames scrambled={scrambled}: {st.segment_ms / st.segment_launches:.3f} ms per launch")
     assert st.segment_ms / st.segment_launches < 2000.0
+
+
+def test_frame_log_is_reused_after_videos_close():
+    """A long-running context (watch mode, many streams) never sees a moment without open videos, so the frame log
+    cannot wait for one to rewind: frames of closed videos are reused first-fit, a video's frames may wrap around the
+    log in several extents, and only a log whose every frame belongs to an open video reports MSCAN_ERR_CAPACITY."""
+    p = kats.env_params()
+    spec = ms.synth_preset(3, 9)
+    cnt, off, recs, pts = ms.synth_host(spec, 0, 200)
+    cfg = cfg_for(p, spec.width, spec.height)
+    of, oc = orc.scan_frames(cfg, recs, off, threads=4)
+
+    def feed(ctx, vid, a, b):
+        ctx.submit(vid, pts[a:b], cnt[a:b], recs[int(off[a]) : int(off[b])])
+
+    with ms.Context(0, p, max_log_frames=64, slab_bytes=8 << 20) as ctx:
+        for v in (1, 2, 3):
+            ctx.video_open(v, spec.width, spec.height)
+        feed(ctx, 1, 0, 40)
+        feed(ctx, 2, 40, 60)          # log: [1: 0..40) [2: 40..60) free 60..64
+        ctx.video_close(1)            # frees 0..40 while video 2 stays open
+        feed(ctx, 3, 100, 130)        # 4 frames at 60..64, then wraps into 0..26
+        f3, c3 = ctx.collect(3)
+        assert np.array_equal(c3, oc[100:130]) and np.array_equal(f3, of[100:130])
+        f2, c2 = ctx.collect(2)
+        assert np.array_equal(c2, oc[40:60]) and np.array_equal(f2, of[40:60])  # untouched by the reuse
+        segs3, res3 = ctx.motion_segments(3, 30 / spec.fps)
+        osegs, ores = orc.video_tail(pts[100:130], of[100:130], 30 / spec.fps, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+        assert segs3.tobytes() == osegs.tobytes() and res3.n_motion_frames == ores.n_motion_frames
+        feed(ctx, 2, 60, 74)          # fills 26..40: the log is now completely owned by videos 2 and 3
+        with pytest.raises(ms.MscanError) as e:
+            feed(ctx, 3, 130, 131)
+        assert e.value.code == ms.ERR_CAPACITY
+        ctx.video_close(3)            # 30 frames come back
+        ctx.video_open(4, spec.width, spec.height)
+        feed(ctx, 4, 150, 180)
+        f4, c4 = ctx.collect(4)
+        assert np.array_equal(c4, oc[150:180]) and np.array_equal(f4, of[150:180])
+        f2, c2 = ctx.collect(2)
+        assert np.array_equal(c2, np.concatenate([oc[40:60], oc[60:74]]))
+        # many generations: the context never has zero open videos, the log (64 frames) is recycled ~30 times
+        ctx.video_close(4)
+        ctx.video_close(2)
+        ctx.video_open(100, spec.width, spec.height)
+        for g in range(60):
+            ctx.video_open(101 + g, spec.width, spec.height)
+            a = (g * 7) % 150
+            feed(ctx, 101 + g, a, a + 29)  # two generations are alive at a time: 58 of the 64 log frames
+            fg, cg = ctx.collect(101 + g)
+            assert np.array_equal(cg, oc[a : a + 29]) and np.array_equal(fg, of[a : a + 29]), g
+            ctx.video_close(100 + g)  # the previous generation goes, this one stays open
