@@ -21,6 +21,8 @@
  *   mscan_segments[_batch]  <- merge/segment/decision block src/pipeline.cpp:297-404
  *                              (sort+unique :302-304, no-motion :308-319, builder :325-344,
  *                              clamp+savings :349-356, decision :358-404)
+ *   mscan_video_append_from <- the union of chunk results `results.extract()` src/pipeline.cpp:268 (+ src/task_queue.cpp:43-57)
+ *                              when the chunks of one video were scanned by different GPUs
  *   mscan_scan_device / mscan_segments_device
  *                           <- same two islands on caller-owned device memory (decode-free
  *                              stream benchmark, BASELINE.json configs[4])
