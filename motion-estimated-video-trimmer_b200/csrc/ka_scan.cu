@@ -416,6 +416,8 @@ bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, 
   plan->cluster = 0;
   plan->cells = cells;
   plan->bit_words = words;
+  plan->full_cells = cells;
+  plan->full_bit_words = words;
   if (ok && !plan->global_cnt) return true;
   if (env_u32("MSCAN_KA_NO_CLUSTER")) return ok;
   // The grid does not fit one CTA: distribute it over a cluster's shared memory in row bands (ka_scan_cluster.cu).

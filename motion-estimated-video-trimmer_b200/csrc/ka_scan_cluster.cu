@@ -16,6 +16,8 @@
 //     queue popped by CTA 0 and published to the cluster one frame ahead.
 // Before this kernel such grids used per-CTA counters in global memory (L2 atomics): 2.3 TB/s at 8K against
 // 7.5 TB/s for grids that fit (tools/ka_bigframe.py). That path remains for grids beyond 16 CTAs of shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -344,6 +346,7 @@ cudaError_t scan_cluster_configure(uint32_t smem_optin) {
 
 cudaError_t scan_cluster_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
+  if (std::getenv("MSCAN_KA_FAIL_CLUSTER_LAUNCH")) return cudaErrorLaunchOutOfResources;  // exercises the caller's fallback
   const uint32_t C = plan.cluster;
   uint32_t clusters = (uint32_t)num_sms / C;
   if (clusters > a.n_frames) clusters = a.n_frames;

@@ -50,6 +50,7 @@ struct ScanPlan {
   uint32_t cluster;     // 0, or the cluster size (2/4/8) of ka_scan_cluster.cu: the grid lives in DSMEM row bands
   uint32_t cells;       // → ScanArgs.max_cells (whole grid, or one band under a cluster plan)
   uint32_t bit_words;   // → ScanArgs.max_bit_words
+  uint32_t full_cells, full_bit_words;  // the whole largest grid (what a non-cluster plan would need)
 };
 
 // Chooses ring depth / occupancy for the largest geometry and the record layout; false if it cannot fit.

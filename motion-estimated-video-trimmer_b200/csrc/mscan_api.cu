@@ -449,7 +449,24 @@ int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaSt
     ev = get_events(c, 0);
     cudaEventRecord(ev.a, st);
   }
-  CU(scan_launch(a, plan, c->num_sms, st));
+  cudaError_t le = scan_launch(a, plan, c->num_sms, st);
+  if (le != cudaSuccess && plan.cluster) {
+    // the device would not place the cluster (partitioned GPU, co-tenants): scan with per-CTA counters in global memory
+    cudaGetLastError();
+    ScanPlan fb;
+    if (!scan_plan(plan.full_cells, plan.full_bit_words, c->smem_optin, a.packed != 0, &fb) || !fb.global_cnt)
+      return fail(c, MSCAN_ERR_CUDA, "cluster launch failed (%s) and the grid has no single-CTA plan", cudaGetErrorString(le));
+    fb.cluster = 0;
+    fb.cells = plan.full_cells;
+    fb.bit_words = plan.full_bit_words;
+    ScanArgs b = args_in;
+    b.stages = fb.stages;
+    b.max_cells = fb.cells;
+    b.max_bit_words = fb.bit_words;
+    if (c->profiling) c->ev_free.push_back(ev);
+    return run_scan(c, b, fb, st, n_recs, slab_index);
+  }
+  CU(le);
   if (c->profiling) {
     cudaEventRecord(ev.b, st);
     c->ev_pending.push_back(ev);

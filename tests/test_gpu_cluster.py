@@ -135,12 +135,13 @@ with ms.Context(0, p) as ctx:
     print(json.dumps({str(v): [ctx.collect(v)[1].tolist()] for v in shapes}))
 """ % (str(ROOT / "motion-estimated-video-trimmer_b200"), str(ROOT / "tests"))
     outs = []
-    for no_cluster in ("0", "1"):
-        env = dict(os.environ, MSCAN_KA_NO_CLUSTER=no_cluster)
+    # cluster plan / global-counter plan / cluster plan whose launch is refused (falls back at launch time)
+    for extra in ({"MSCAN_KA_NO_CLUSTER": "0"}, {"MSCAN_KA_NO_CLUSTER": "1"}, {"MSCAN_KA_FAIL_CLUSTER_LAUNCH": "1"}):
+        env = dict(os.environ, **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(r.stdout.strip().splitlines()[-1])
-    assert outs[0] == outs[1]
+    assert outs[0] == outs[1] == outs[2]
     # and against the oracle (same seed, regenerated here)
     import json
 
