@@ -613,7 +613,7 @@ def main():
     ap.add_argument("--records", type=float, default=1e9, help="records per GPU in the device-resident stream (stream1e9)")
     ap.add_argument("--e2e-records", type=float, default=9e7, help="records of the host-resident e2e sample (~3.6 GB pinned)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="override: frames of the e2e sample")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-records", type=float, default=3e7, help="records of the CPU-baseline / reference-arm sample")
     ap.add_argument("--cpu-frames", type=int, default=0, help="override: frames of the CPU sample")
     ap.add_argument("--slab-mb", type=int, default=64)
