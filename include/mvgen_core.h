@@ -40,6 +40,9 @@ typedef struct mvgen_spec {
   uint32_t p_dense_move;    /* /1024: 4x4-MB tiles moving in dense mode                    */
   int32_t static_a0, static_a1, static_b0, static_b1; /* forced-static local frame ranges  */
   double fps;
+  int32_t scatter;          /* 1: SURVEY §8(d) config-5 shape — every MB exports 2 records whose dst is a uniformly
+                               random MB sub-centre of the picture (no raster order, no spatial coherence)      */
+  uint32_t p_rec_move;      /* /65536 per record (scatter mode): moving, d uniform in [-8,8]^2               */
 } mvgen_spec;
 
 /* Per-frame state: which blobs are alive and where (MB units). */
@@ -57,7 +60,7 @@ typedef struct mvgen_frame {
 } mvgen_frame;
 
 /* Per-macroblock decision. kind: 0 static 16x16, 1 static 2-part, 2 noise 8x8, 3 single moving,
- * 4 blob 8x8, 5 dense static 8x8, 6 dense moving 8x8. */
+ * 4 blob 8x8, 5 dense static 8x8, 6 dense moving 8x8, 7 scattered (position and motion drawn per record). */
 typedef struct mvgen_mb {
   int32_t nrec;
   int32_t kind;
@@ -143,6 +146,11 @@ MVGEN_HD void mvgen_mb_eval(const mvgen_spec* s, const mvgen_frame* fr, int32_t 
   const uint64_t mbid = (uint64_t)my * (uint64_t)fr->mbw + (uint64_t)mx;
   const uint64_t h = mvgen_hash(s->seed, fr->gframe, mbid, 0x4D42ull);
   m->h = h;
+  if (s->scatter) {
+    m->nrec = 2;
+    m->kind = 7;
+    return;
+  }
   if (s->dense) {
     m->nrec = 4;
     /* moving areas are 4x4-MB tiles that persist for 8 frames → spatially adjacent active cells */
@@ -234,6 +242,20 @@ MVGEN_HD void mvgen_record(const mvgen_spec* s, const mvgen_mb* m, int32_t mx, i
   }
   int32_t X = (mx << 4) + ox;
   int32_t Y = (my << 4) + oy;
+  if (m->kind == 7) { /* scattered: dst uniform over the picture's 8x8 sub-centres, 10 % moving uniformly */
+    const uint64_t hp = mvgen_mix(hk ^ 0x5CA77E2ull);
+    const int32_t mbw = (s->width + 15) >> 4, mbh = (s->height + 15) >> 4;
+    X = ((int32_t)(hp % (uint64_t)mbw) << 4) + (((hp >> 40) & 1u) ? 12 : 4);
+    Y = ((int32_t)((hp >> 20) % (uint64_t)mbh) << 4) + (((hp >> 41) & 1u) ? 12 : 4);
+    w = 8;
+    h = 8;
+    dx = 0;
+    dy = 0;
+    if ((uint32_t)((hp >> 44) & 0xFFFFu) < s->p_rec_move) {
+      dx = (int32_t)((hk >> 32) % 17u) - 8;
+      dy = (int32_t)((hk >> 40) % 17u) - 8;
+    }
+  }
   if ((uint32_t)((hk >> 16) & 0xFFFFu) < s->p_oob) {
     const uint32_t mode = (uint32_t)(hk >> 32) & 3u;
     const int32_t off = (int32_t)((hk >> 34) & 31u);
@@ -271,6 +293,15 @@ MVGEN_HD void mvgen_preset(mvgen_spec* s, int config, uint64_t seed) {
   s->p_dense_move = 0;
   s->static_a0 = s->static_a1 = s->static_b0 = s->static_b1 = 0;
   s->fps = 30.0;
+  s->scatter = 0;
+  s->p_rec_move = 0;
+  if (config == 5) { /* SURVEY §8(d) config 5 as specified: 16 320 records per frame, uniform dst, 10 % moving, 0.1 % OOB */
+    s->gop = 0;
+    s->frames_per_video = 18000;
+    s->scatter = 1;
+    s->p_rec_move = 6554; /* 10 % */
+    return;
+  }
   if (config == 0) { /* 60 s 1080p30, static spans [300,900) and [1200,1500) */
     s->frames_per_video = 1800;
     s->p_window_active = 1024;

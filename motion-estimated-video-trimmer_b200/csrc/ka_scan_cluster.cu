@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(kThreads, 1) ka_scan_cluster_kernel(const __gr
       continue;
     }
     const uint32_t rpr = ((uint32_t)gh + C - 1) / C;                 // rows per band
-    const uint32_t rpr_inv = (uint32_t)(0x100000000ull / rpr) + 1u;  // exact gy / rpr for gy < 2^16
+    // exact gy / rpr for gy < 2^16 and rpr >= 2; rpr == 1 (a grid with no more rows than the cluster has CTAs, e.g. a
+    // QVGA video sharing a context with a 16K one) would wrap the reciprocal to 1: the owner is then gy itself
+    const uint32_t rpr_inv = (uint32_t)(0x100000000ull / rpr) + 1u;
     const uint32_t row0 = rank * rpr;
     const uint32_t rows = row0 < (uint32_t)gh ? min(rpr, (uint32_t)gh - row0) : 0u;
     const uint32_t wpr = ((uint32_t)gw + 31u) >> 5;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(kThreads, 1) ka_scan_cluster_kernel(const __gr
             if (head && key >= 0) {
               const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
               const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
-              const uint32_t owner = __umulhi((uint32_t)gy, rpr_inv);
+              const uint32_t owner = rpr == 1u ? (uint32_t)gy : __umulhi((uint32_t)gy, rpr_inv);
               const uint32_t lkey = ((uint32_t)gy - owner * rpr) * (uint32_t)gw + (uint32_t)gx;
               const uint32_t sh = (lkey & 1u) * 16u;
               const uint32_t word = cnt_addr + 4u * (lkey >> 1);

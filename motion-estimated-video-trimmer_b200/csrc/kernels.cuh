@@ -91,6 +91,9 @@ struct SegArgs {
 };
 cudaError_t segments_launch(const SegArgs& a, uint32_t n_videos, cudaStream_t st);
 
+// ---- host side: projection of native records to mscan_mv8 (host_project.cpp; plain C++ with AVX-512 paths)
+void project_records(const uint8_t* in, uint64_t n, uint64_t* out);
+
 // ---- aux: exclusive scan of per-frame record counts, synthetic stream generation
 cudaError_t offsets_launch(const uint32_t* counts, uint32_t n, uint64_t* off, uint64_t* block_scratch,
                            cudaStream_t st);

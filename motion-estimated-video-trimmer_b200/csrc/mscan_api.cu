@@ -8,10 +8,19 @@
 //                   while slab k is being DMA'd and scanned, submit() fills slab k+1
 //                   (memory_io.cpp role: the reference mmaps the file for FFmpeg; here the staged
 //                   thing is the decoder's MV side data on its way to HBM);
+//   * submit      — reserve / fill / commit: a call reserves its byte range, frame slots and log range
+//                   under the context mutex (a few hundred ns), fills the reserved range of the pinned
+//                   staging OUTSIDE the mutex, and commits with an atomic. Many decode threads therefore
+//                   project their own cache-hot side data concurrently (one scanner per decode thread,
+//                   include/motion_trim/motion_scanner.hpp:8-13, workers at src/pipeline.cpp:186-235);
+//                   staged bytes go to the GPU in copy windows as soon as every writer of a window
+//                   has committed, so the link works while the slab is still filling;
 //   * projection  — native records in pageable memory are not memcpy'd into staging: only bytes 6..13
-//                   of each 40-byte record (the four int16 the path reads) are written there, by a
-//                   small worker pool for large submits, so 8 B/record cross PCIe instead of 40;
-//   * K-A per slab, K-C per segments call.
+//                   of each 40-byte record (the four int16 the path reads) are written there (by the
+//                   process-wide worker pool for large submits), so 8 B/record cross PCIe instead of 40;
+//   * tails       — collect / segments / close wait only for the slabs that hold frames of the videos
+//                   in the call, outside the mutex: one stream's tail does not stall the others;
+//   * K-A per slab segment, K-C per segments call.
 // There is no CPU implementation of the path behind this ABI.
 #include <cuda_runtime.h>
 
@@ -34,6 +43,7 @@
 #include <memory>
 #include <mutex>
 #include <new>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -50,13 +60,18 @@ constexpr int kWorkSlots = 16;  // frame queues: one per slab stream (launches o
 constexpr uint32_t kMaxGeoms = 4096;
 
 struct Extent {
-  uint64_t start, n;
+  uint64_t start, n;  // frames [start, start+n) of the frame log
+  uint64_t vpos;      // index of the extent's first frame in the video's submission order (a submit call reserves
+                      // its index range up front, so concurrent submits to one video keep each call's frames together)
 };
 
 struct Video {
   uint32_t geom = 0;
   uint64_t n_frames = 0;
   std::vector<Extent> extents;
+  // epoch of each slab when this video last put frames into it: equal to the slab's current epoch ⇔ results
+  // of this video may still be pending there (what collect / segments / close have to wait for — nothing else)
+  uint64_t slab_epoch[kSlabs] = {0, 0, 0};
 };
 
 struct Slab {
@@ -81,6 +96,14 @@ struct Slab {
   uint64_t seg_byte0 = 0;     // 256-byte aligned offset of the open segment's first record
   uint64_t seg_recs = 0;
   uint64_t seg_log_base = 0;  // frame-log index of the open segment's first frame
+  // ---- concurrent fill (reserve under ctx->mu, fill outside, commit with atomics) ----
+  bool staged = false;                 // the open segment's records pass through h_recs (else DMA'd from caller memory)
+  uint64_t epoch = 1;                  // bumped by every recycle
+  uint64_t launch_seq = 0;             // bumped by every K-A launch on this slab
+  std::atomic<uint32_t> writers{0};    // reservations of the open segment whose fill has not been committed
+  std::unique_ptr<std::atomic<int32_t>[]> pend;  // per copy window: uncommitted reservations that touch it
+  std::atomic<uint64_t> reserved_end{0};         // == bytes, published for the copy pump
+  uint64_t copy_head = 0;              // (ctx->issue_mu) staged bytes of the open segment below this are on their way
 };
 
 struct EvPair {
@@ -88,48 +111,20 @@ struct EvPair {
   int kind;  // 0 = K-A, 1 = K-C
 };
 
-// ---- host projection AVMotionVector → mscan_mv8 -------------------------------------------------
-// Bytes 6..13 of a native record are src_x, src_y, dst_x, dst_y (motion_scanner.cpp:243-256 reads
-// nothing else), contiguous: the projection is one unaligned 8-byte load and one store per record.
-// Streaming stores: the staging buffer is read next by the DMA engine, not by this core.
-void project_records(const uint8_t* in, uint64_t n, uint64_t* out) {
-  for (uint64_t i = 0; i < n; ++i) {
-#if defined(__x86_64__)
-    // 8 records = 5 cache lines; software prefetch 4 KB ahead measured +13 % from DRAM on the B200 box's
-    // host (tools/exp_hostfeed.cu), free when the source is cache-hot. Prefetches never fault.
-    if ((i & 7u) == 0) {
-      const char* q = reinterpret_cast<const char*>(in + (size_t)kRecBytes * i + 4096);
-      _mm_prefetch(q, _MM_HINT_T0);
-      _mm_prefetch(q + 64, _MM_HINT_T0);
-      _mm_prefetch(q + 128, _MM_HINT_T0);
-      _mm_prefetch(q + 192, _MM_HINT_T0);
-      _mm_prefetch(q + 256, _MM_HINT_T0);
-    }
-#endif
-    uint64_t v;
-    std::memcpy(&v, in + (size_t)kRecBytes * i + 6, sizeof v);
-#if defined(__x86_64__)
-    _mm_stream_si64(reinterpret_cast<long long*>(out + i), (long long)v);
-#else
-    out[i] = v;
-#endif
-  }
-#if defined(__x86_64__)
-  _mm_sfence();
-#endif
-}
+// ---- host projection AVMotionVector → mscan_mv8: mscan::project_records, csrc/host_project.cpp ----------------
 
 constexpr uint64_t kPoolChunk = 32768;      // records per work item (1.3 MB of native records)
 constexpr uint64_t kPoolMinRecs = 1 << 18;  // smaller jobs are projected by the calling thread alone
 
-// Parallel-for over one projection job; the calling thread takes part. One job at a time (callers
-// hold the context mutex).
+// Parallel-for over one projection job; the calling thread takes part. ONE pool per process, shared by every
+// context (a pool per GPU context sized for the whole box would oversubscribe it n-fold, one sized cores/n would
+// leave cores idle whenever the GPUs are not all projecting): jobs are serialised, each may use up to `limit` threads.
 class PackPool {
  public:
   // Starts up to `workers` threads; if the platform refuses some, the pool simply runs with fewer.
   explicit PackPool(int workers) noexcept {
     try {
-      for (int i = 0; i < workers; ++i) th_.emplace_back([this] { worker(); });
+      for (int i = 0; i < workers; ++i) th_.emplace_back([this, i] { worker(i); });
     } catch (...) {
     }
   }
@@ -143,7 +138,9 @@ class PackPool {
   }
   int workers() const { return (int)th_.size(); }
 
-  void run(const uint8_t* src, uint64_t* dst, uint64_t n) {
+  // `limit`: threads that may work on this job, the caller included (<= 0: all).
+  void run(const uint8_t* src, uint64_t* dst, uint64_t n, int limit) {
+    std::lock_guard<std::mutex> job(job_mu_);
     const uint64_t total = (n + kPoolChunk - 1) / kPoolChunk;
     {
       std::unique_lock<std::mutex> lk(mu_);
@@ -152,6 +149,7 @@ class PackPool {
       dst_ = dst;
       n_ = n;
       total_ = total;
+      limit_ = limit <= 0 ? (int)th_.size() : std::min((int)th_.size(), limit - 1);
       next_.store(0, std::memory_order_relaxed);
       done_.store(0, std::memory_order_relaxed);
       ++gen_;
@@ -170,7 +168,7 @@ class PackPool {
       done_.fetch_add(1, std::memory_order_release);
     }
   }
-  void worker() {
+  void worker(int index) {
     uint64_t seen = 0;
     for (;;) {
       const uint8_t* src;
@@ -180,6 +178,7 @@ class PackPool {
         cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
         if (stop_) return;
         seen = gen_;
+        if (index >= limit_) continue;  // this job runs with fewer threads
         src = src_;
         dst = dst_;
         n = n_;
@@ -196,11 +195,11 @@ class PackPool {
   }
 
   std::vector<std::thread> th_;
-  std::mutex mu_;
+  std::mutex mu_, job_mu_;
   std::condition_variable cv_, idle_cv_;
   bool stop_ = false;
   uint64_t gen_ = 0;
-  int active_ = 0;
+  int active_ = 0, limit_ = 0;
   const uint8_t* src_ = nullptr;
   uint64_t* dst_ = nullptr;
   uint64_t n_ = 0, total_ = 0;
@@ -216,6 +215,50 @@ int default_pack_threads() {
   return std::max(1, std::min(n, 64));
 }
 
+// The process-wide pool, created at the first large projection (never destroyed: worker threads must not be
+// joined from a static destructor of a dlopen'ed library).
+PackPool* shared_pool() {
+  static PackPool* pool = new (std::nothrow) PackPool(default_pack_threads() - 1);
+  return pool;
+}
+
+// Host ranges this library pinned (mscan_host_alloc / mscan_host_register): mscan_submit looks a source pointer up
+// here instead of asking the driver on every call (cudaPointerGetAttributes costs ~1 µs, a per-frame submit from a
+// decode thread is worth less than that). Memory pinned behind the library's back (cudaHostRegister by the caller)
+// is still recognised for submits of at least kAttrQueryBytes, where the driver query is noise.
+constexpr uint64_t kAttrQueryBytes = 1ull << 20;
+class PinnedRanges {
+ public:
+  void add(const void* p, size_t n) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    r_[reinterpret_cast<uintptr_t>(p)] = n;
+    count_.store(r_.size(), std::memory_order_release);
+  }
+  void remove(const void* p) {
+    std::unique_lock<std::shared_mutex> lk(mu_);
+    r_.erase(reinterpret_cast<uintptr_t>(p));
+    count_.store(r_.size(), std::memory_order_release);
+  }
+  bool contains(const void* p, size_t n) {
+    if (count_.load(std::memory_order_acquire) == 0) return false;
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    auto it = r_.upper_bound(a);
+    if (it == r_.begin()) return false;
+    --it;
+    return a >= it->first && a + n <= it->first + it->second;
+  }
+
+ private:
+  std::shared_mutex mu_;
+  std::map<uintptr_t, size_t> r_;
+  std::atomic<size_t> count_{0};
+};
+PinnedRanges& pinned_ranges() {
+  static PinnedRanges* r = new PinnedRanges();
+  return *r;
+}
+
 }  // namespace
 
 struct mscan_ctx {
@@ -223,7 +266,10 @@ struct mscan_ctx {
   int num_sms = 0;
   uint32_t smem_optin = 0;
   mscan_params params{};
-  std::mutex mu;
+  // Lock order: tail_mu → mu → issue_mu. `mu` guards the bookkeeping (videos, frame log, slab fill levels) and is
+  // never held while records are projected or copied; `issue_mu` orders the H2D copies of staged windows with the
+  // K-A launch that consumes them; `tail_mu` serialises K-C (its scratch and main_stream) without blocking submits.
+  std::mutex mu, issue_mu, tail_mu;
   std::string err;
 
   // kernel constants derived from params
@@ -279,8 +325,10 @@ struct mscan_ctx {
 
   // host projection (see project_records)
   int staging_mode = MSCAN_STAGING_AUTO;
-  int pack_threads = 0;  // 0 → default_pack_threads() at first use
-  std::unique_ptr<PackPool> pool;
+  int pack_threads = 0;  // threads of the shared pool one large submit of this context may use; 0 → all
+  uint32_t win_shift = 21;  // log2 of the H2D copy window (2 MiB: 38 µs on a Gen5 x16 link against ~3 µs to enqueue a copy)
+  // counters written outside `mu` (folded into `stats` by mscan_get_stats)
+  std::atomic<uint64_t> a_h2d_bytes{0}, a_records_projected{0}, a_project_ns{0};
 
   // MSCAN_TRACE=1: wall time per ABI entry point (including time spent waiting for the context mutex),
   // printed to stderr by mscan_destroy — the role of the reference's TIMER_START/END + TimingCollector
@@ -326,9 +374,17 @@ int fail(mscan_ctx* c, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(c->trace_mu);  // errors are reported from under different locks
     c->err = buf;
   }
   return code;
+}
+
+// folds the counters that are written outside `mu` into the public stats (caller holds mu)
+void fold_stats(mscan_ctx* c) {
+  c->stats.h2d_bytes += c->a_h2d_bytes.exchange(0, std::memory_order_relaxed);
+  c->stats.records_projected += c->a_records_projected.exchange(0, std::memory_order_relaxed);
+  c->stats.project_ms += (double)c->a_project_ns.exchange(0, std::memory_order_relaxed) * 1e-6;
 }
 
 // No exception crosses the ABI: every entry point that can allocate is a function-try-block ending here.
@@ -487,15 +543,56 @@ ScanArgs base_args(mscan_ctx* c) {
   return a;
 }
 
-// launch K-A on the open segment of a slab and open the next one
+// Copy pump (caller holds issue_mu): enqueues the H2D copy of every staged window of the open segment that is
+// complete — closed (the reservation pointer has moved past its end) and without uncommitted writers. Windows go out
+// in order, so copy_head is the only state; `seal` also sends the partial last window (launch_segment has already
+// waited for the segment's writers). Anyone may pump at any time: the decision depends on the slab's state only.
+int pump_locked(mscan_ctx* c, Slab& s, bool seal) {
+  if (!s.staged) return MSCAN_OK;
+  const uint64_t end_res = s.reserved_end.load(std::memory_order_acquire);
+  while (s.copy_head < end_res) {
+    const uint64_t k = s.copy_head >> c->win_shift, win_end = (k + 1) << c->win_shift;
+    if (!seal && end_res < win_end) break;
+    if (s.pend[k].load(std::memory_order_acquire) != 0) break;
+    const uint64_t e = std::min(win_end, end_res);
+    CU(cudaMemcpyAsync(s.d_recs + s.copy_head, s.h_recs + s.copy_head, e - s.copy_head, cudaMemcpyHostToDevice, s.stream));
+    c->a_h2d_bytes.fetch_add(e - s.copy_head, std::memory_order_relaxed);
+    s.copy_head = e;
+  }
+  return MSCAN_OK;
+}
+
+void try_pump(mscan_ctx* c, Slab& s) {
+  std::unique_lock<std::mutex> lk(c->issue_mu, std::try_to_lock);
+  if (!lk.owns_lock()) return;  // somebody is pumping or launching; launch_segment is the backstop
+  if (cudaSetDevice(c->device) != cudaSuccess) return;
+  pump_locked(c, s, false);
+}
+
+void wait_writers(const Slab& s) {
+  for (uint32_t spin = 0; s.writers.load(std::memory_order_acquire) != 0; ++spin) {
+#if defined(__x86_64__)
+    if (spin < 256) _mm_pause();
+    else std::this_thread::yield();
+#else
+    std::this_thread::yield();
+#endif
+  }
+}
+
+// launch K-A on the open segment of a slab and open the next one (caller holds mu)
 int launch_segment(mscan_ctx* c, Slab& s) {
   const uint32_t n = s.frames - s.seg_frame0;
   if (n == 0) return MSCAN_OK;
+  wait_writers(s);  // fills run outside mu and never need it to commit: this wait is bounded by one frame's projection
+  std::lock_guard<std::mutex> issue(c->issue_mu);
+  int rc = pump_locked(c, s, true);
+  if (rc) return rc;
   s.h_rec_off[s.seg_slot0 + n] = s.seg_recs;
   CU(cudaMemcpyAsync(s.d_rec_off + s.seg_slot0, s.h_rec_off + s.seg_slot0, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(s.d_geom + s.seg_frame0, s.h_geom + s.seg_frame0, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s.stream));
   CU(cudaMemcpyAsync(c->d_pts + s.seg_log_base, s.h_pts + s.seg_frame0, sizeof(double) * n, cudaMemcpyHostToDevice, s.stream));
-  c->stats.h2d_bytes += sizeof(uint64_t) * (n + 1) + 12ull * n;
+  c->a_h2d_bytes.fetch_add(sizeof(uint64_t) * (n + 1) + 12ull * n, std::memory_order_relaxed);
   CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of the slab so far precedes this point
   ScanArgs a = base_args(c);
   a.recs = s.d_recs + s.seg_byte0;
@@ -510,25 +607,34 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   a.stages = plan.stages;
   a.max_cells = plan.cells;
   a.max_bit_words = plan.bit_words;
-  int rc = run_scan(c, a, plan, s.stream, s.seg_recs, (int)(&s - c->slabs));
+  rc = run_scan(c, a, plan, s.stream, s.seg_recs, (int)(&s - c->slabs));
   if (rc) return rc;
   CU(cudaEventRecord(s.done, s.stream));
   s.in_flight = true;
+  s.launch_seq += 1;
   s.seg_frame0 = s.frames;
   s.seg_slot0 += n + 1;
   s.bytes = (s.bytes + 255) & ~255ull;
   s.seg_byte0 = s.bytes;
   s.seg_recs = 0;
+  s.staged = false;
+  s.reserved_end.store(s.bytes, std::memory_order_release);
+  s.copy_head = s.bytes;
   return MSCAN_OK;
 }
 
-void recycle_slab(Slab& s) {
+void recycle_slab(mscan_ctx* c, Slab& s) {
+  std::lock_guard<std::mutex> issue(c->issue_mu);  // a late try_pump may be looking at copy_head
   s.bytes = 0;
   s.frames = 0;
   s.seg_frame0 = 0;
   s.seg_slot0 = 0;
   s.seg_byte0 = 0;
   s.seg_recs = 0;
+  s.staged = false;
+  s.copy_head = 0;
+  s.reserved_end.store(0, std::memory_order_release);
+  s.epoch += 1;
 }
 
 int wait_slab(mscan_ctx* c, Slab& s) {
@@ -536,7 +642,7 @@ int wait_slab(mscan_ctx* c, Slab& s) {
     CU(cudaEventSynchronize(s.done));
     s.in_flight = false;
   }
-  recycle_slab(s);
+  recycle_slab(c, s);
   return MSCAN_OK;
 }
 
@@ -557,8 +663,51 @@ int sync_scans_locked(mscan_ctx* c) {
     if (s.in_flight) {
       CU(cudaEventSynchronize(s.done));
       s.in_flight = false;
-      if (&s != &c->slabs[c->cur]) recycle_slab(s);
+      if (&s != &c->slabs[c->cur]) recycle_slab(c, s);
     }
+  return MSCAN_OK;
+}
+
+// Waits until every frame the listed videos have submitted so far has its results in the frame log — and for nothing
+// else: only slabs that hold frames of these videos are launched / waited for, and the waiting happens with `mu`
+// released, so the decode threads of other videos keep submitting (the reference's workers never wait for each
+// other either, src/pipeline.cpp:186-235). `lk` holds c->mu on entry and on return; iterators into c->videos are
+// invalid afterwards.
+int sync_videos(mscan_ctx* c, std::unique_lock<std::mutex>& lk, const uint32_t* ids, uint32_t n_ids) {
+  struct Wait {
+    int k;
+    uint64_t epoch, seq;
+    cudaEvent_t ev;
+  };
+  Wait waits[kSlabs];
+  int n_wait = 0;
+  for (int k = 0; k < kSlabs; ++k) {
+    Slab& s = c->slabs[k];
+    bool mine = false;
+    for (uint32_t i = 0; i < n_ids && !mine; ++i) {
+      auto it = c->videos.find(ids[i]);
+      mine = it != c->videos.end() && it->second.slab_epoch[k] == s.epoch;
+    }
+    if (!mine) continue;
+    if (s.frames > s.seg_frame0) {  // an open segment (only the current slab has one): launch it, keep filling the slab
+      int rc = launch_segment(c, s);
+      if (rc) return rc;
+    }
+    if (s.in_flight) waits[n_wait++] = Wait{k, s.epoch, s.launch_seq, s.done};
+  }
+  if (n_wait == 0) return MSCAN_OK;
+  lk.unlock();
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n_wait && e == cudaSuccess; ++i) e = cudaEventSynchronize(waits[i].ev);
+  lk.lock();
+  if (e != cudaSuccess) return fail(c, MSCAN_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+  for (int i = 0; i < n_wait; ++i) {
+    Slab& s = c->slabs[waits[i].k];
+    if (s.epoch == waits[i].epoch && s.launch_seq == waits[i].seq && s.in_flight) {  // nothing was launched on it meanwhile
+      s.in_flight = false;
+      if (waits[i].k != c->cur) recycle_slab(c, s);
+    }
+  }
   return MSCAN_OK;
 }
 
@@ -799,6 +948,12 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   c->log_limit = c->log_cap;
   c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (64ull << 20);
   c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
+  if (const char* w = std::getenv("MSCAN_COPY_WINDOW_KB")) {  // experiments: H2D copy window, rounded down to a power of two
+    const long kb = std::atol(w);
+    uint32_t sh = 16;
+    while (sh < 30 && (2ull << sh) <= (uint64_t)std::max(64l, kb) * 1024ull) ++sh;
+    c->win_shift = sh;
+  }
 
   auto bail = [&](int code) {
     mscan_destroy(c);
@@ -826,6 +981,10 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   CUB_(cudaMalloc((void**)&c->d_flags, c->log_cap));
   CUB_(cudaMalloc((void**)&c->d_counts, sizeof(uint32_t) * c->log_cap));
   for (auto& s : c->slabs) {
+    const size_t n_win = (size_t)((c->slab_bytes + 256) >> c->win_shift) + 2;
+    s.pend.reset(new (std::nothrow) std::atomic<int32_t>[n_win]);
+    if (!s.pend) return bail(MSCAN_ERR_NOMEM);
+    for (size_t k = 0; k < n_win; ++k) s.pend[k].store(0, std::memory_order_relaxed);
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
@@ -843,6 +1002,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
 
 int mscan_destroy(mscan_ctx* c) {
   if (!c) return MSCAN_OK;
+  fold_stats(c);
   if (c->trace && !c->api_times.empty()) {
     std::fprintf(stderr, "[mscan trace] device %d: wall time per entry point (lock waits included)\n", c->device);
     for (const auto& kv : c->api_times)
@@ -923,6 +1083,7 @@ int mscan_get_stats(mscan_ctx* c, mscan_stats* s) try {
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
   drain_events(c);
+  fold_stats(c);
   *s = c->stats;
   return MSCAN_OK;
 } catch (...) {
@@ -934,6 +1095,7 @@ int mscan_reset_stats(mscan_ctx* c) try {
   std::lock_guard<std::mutex> lk(c->mu);
   cudaSetDevice(c->device);
   drain_events(c);
+  fold_stats(c);
   c->stats = mscan_stats{};
   return MSCAN_OK;
 } catch (...) {
@@ -984,6 +1146,46 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
   return mscan_video_open_geometry(c, video_id, &g);
 }
 
+// How one reservation gets its records into the slab (decided under mu, executed outside it).
+enum FillKind { kFillNone = 0, kFillProject, kFillMemcpy, kFillInPlace };
+
+// Executes one reservation's fill outside the context mutex, then commits it.
+static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, uint64_t nbytes, const uint8_t* from,
+                           uint64_t n_recs) {
+  int rc = MSCAN_OK;
+  if (kind == kFillProject) {
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t* to = reinterpret_cast<uint64_t*>(s.h_recs + off);
+    PackPool* pool = n_recs >= kPoolMinRecs ? shared_pool() : nullptr;
+    if (pool && pool->workers() > 0 && c->pack_threads != 1) pool->run(from, to, n_recs, c->pack_threads);
+    else project_records(from, n_recs, to);
+    c->a_project_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                              std::memory_order_relaxed);
+    c->a_records_projected.fetch_add(n_recs, std::memory_order_relaxed);
+  } else if (kind == kFillMemcpy) {
+    std::memcpy(s.h_recs + off, from, nbytes);
+  } else if (kind == kFillInPlace) {
+    std::lock_guard<std::mutex> issue(c->issue_mu);
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_recs + off, from, nbytes, cudaMemcpyHostToDevice, s.stream);
+    if (e != cudaSuccess) rc = MSCAN_ERR_CUDA;
+    c->a_h2d_bytes.fetch_add(nbytes, std::memory_order_relaxed);
+  }
+  // commit: the windows first, then the segment's writer count (launch_segment waits for the latter)
+  bool completed_window = false;
+  if (kind == kFillProject || kind == kFillMemcpy) {
+    std::atomic_thread_fence(std::memory_order_release);
+    for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
+      if (s.pend[k].fetch_sub(1, std::memory_order_acq_rel) == 1) completed_window = true;
+  }
+  const uint64_t end_res = s.reserved_end.load(std::memory_order_acquire);
+  s.writers.fetch_sub(1, std::memory_order_release);
+  // after the decrement `s` may be launched and recycled by another thread at any moment; pumping is state-based
+  // and therefore still safe (it then finds nothing, or windows of the slab's next life)
+  if (completed_window && (end_res >> c->win_shift) > (off >> c->win_shift)) try_pump(c, s);
+  return rc;
+}
+
 // Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
 static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
                        const void* recs, bool src_packed, uint64_t* first_frame_out) try {
@@ -998,14 +1200,41 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     return MSCAN_OK;
   }
   if (!pts || !rec_count) return fail(c, MSCAN_ERR_INVALID, "null pts/rec_count");
-  std::lock_guard<std::mutex> lk(c->mu);
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(recs);
+  const uint64_t in_stride = src_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
+  // is the source pinned? (before taking the mutex; see PinnedRanges)
+  bool pinned = false;
+  if (recs) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_frames; ++i) total += rec_count[i];
+    const uint64_t src_bytes = total * in_stride;
+    if (src_bytes) {
+      pinned = pinned_ranges().contains(recs, src_bytes);
+      if (!pinned && src_bytes >= kAttrQueryBytes) pinned = is_pinned(recs);
+    }
+  }
+  std::unique_lock<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
-  Video& v = it->second;
-  if (first_frame_out) *first_frame_out = v.n_frames;
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(recs);
-  const bool pinned = recs && is_pinned(recs);
+  const uint64_t vbase = it->second.n_frames;  // this call owns video-local indices [vbase, vbase + n_frames)
+  it->second.n_frames += n_frames;
+  if (first_frame_out) *first_frame_out = vbase;
+  // on failure the indices not yet backed by log frames are given back (when no later call has reserved behind them)
+  struct Rollback {
+    mscan_ctx* c;
+    std::unique_lock<std::mutex>& lk;
+    uint32_t video_id, n_frames;
+    const uint32_t& f;
+    uint64_t vbase;
+    bool armed = true;
+    ~Rollback() {
+      if (!armed || f >= n_frames) return;
+      if (!lk.owns_lock()) lk.lock();
+      auto it = c->videos.find(video_id);
+      if (it != c->videos.end() && it->second.n_frames == vbase + n_frames) it->second.n_frames = vbase + f;
+    }
+  };
   // How the records reach the slab: native+pinned → DMA in place (40 B/record over PCIe, no host work);
   // native+pageable → the staging pass writes only the 8 bytes the path reads (8 B/record over PCIe);
   // packed → as is (DMA in place when pinned, memcpy into staging otherwise).
@@ -1016,15 +1245,23 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     else project = !pinned;
   }
   const bool slab_packed = src_packed || project;
-  const uint64_t in_stride = src_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
+  const bool staged = project || !pinned;
+  const FillKind kind = project ? kFillProject : (pinned ? kFillInPlace : kFillMemcpy);
   const uint64_t out_stride = slab_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
-  // projected sub-batches are DMA'd as they are produced, so the copy of one overlaps the projection of the next
+  // large projected submits go out in sub-batches, so the copy of one overlaps the projection of the next
   const uint64_t max_take_recs = project ? (4ull << 20) : ~0ull;
   uint32_t f = 0;
   uint64_t src_rec = 0;
+  int result = MSCAN_OK;
+  Rollback rollback{c, lk, video_id, n_frames, f, vbase};
   while (f < n_frames) {
+    // (re)validate the video: the mutex was released while the previous piece was being filled
+    it = c->videos.find(video_id);
+    if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during a submit", video_id);
+    Video& v = it->second;
     Slab* s = &c->slabs[c->cur];
-    if (s->frames > s->seg_frame0 && s->packed != slab_packed) {  // one record format per segment (K-A launch)
+    if (s->frames > s->seg_frame0 && (s->packed != slab_packed || s->staged != staged)) {
+      // one record format and one route (staging / in-place DMA) per segment (= one K-A launch)
       int rc = launch_segment(c, *s);
       if (rc) return rc;
     }
@@ -1055,40 +1292,18 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       if (rc) return rc;
       continue;
     }
-    if (s->frames == s->seg_frame0) {
+    const uint64_t nbytes = take_recs * out_stride;
+    if (nbytes && !recs) return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
+    if (s->frames == s->seg_frame0) {  // this reservation opens the segment
       s->seg_log_base = c->log_head;
       s->packed = slab_packed;
+      std::lock_guard<std::mutex> issue(c->issue_mu);
+      s->staged = staged;
+      s->copy_head = s->seg_byte0;
     }
-    const uint64_t nbytes = take_recs * out_stride;
-    if (nbytes) {
-      if (!recs) return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
-      const uint8_t* from = src + src_rec * in_stride;
-      if (!project && pinned) {
-        CU(cudaMemcpyAsync(s->d_recs + s->bytes, from, nbytes, cudaMemcpyHostToDevice, s->stream));
-      } else {
-        if (!s->h_recs) CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
-        if (project) {
-          const auto t0 = std::chrono::steady_clock::now();
-          uint64_t* to = reinterpret_cast<uint64_t*>(s->h_recs + s->bytes);
-          if (take_recs >= kPoolMinRecs) {
-            if (!c->pool) {
-              const int nthr = c->pack_threads > 0 ? c->pack_threads : default_pack_threads();
-              c->pool.reset(new (std::nothrow) PackPool(nthr - 1));
-            }
-            if (c->pool && c->pool->workers() > 0) c->pool->run(from, to, take_recs);
-            else project_records(from, take_recs, to);
-          } else {
-            project_records(from, take_recs, to);
-          }
-          c->stats.project_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-          c->stats.records_projected += take_recs;
-        } else {
-          std::memcpy(s->h_recs + s->bytes, from, nbytes);
-        }
-        CU(cudaMemcpyAsync(s->d_recs + s->bytes, s->h_recs + s->bytes, nbytes, cudaMemcpyHostToDevice, s->stream));
-      }
-      c->stats.h2d_bytes += nbytes;
-    }
+    if (staged && nbytes && !s->h_recs) CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
+    // ---- reserve: byte range, frame slots, log range --------------------------------------------------
+    const uint64_t off = s->bytes;
     uint64_t r = s->seg_recs;
     const uint32_t slot = s->seg_slot0 + (s->frames - s->seg_frame0);
     for (uint32_t i = 0; i < take; ++i) {
@@ -1098,22 +1313,46 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       s->h_pts[s->frames + i] = pts[f + i];
     }
     // extend the video's last extent when contiguous in the log
-    const uint64_t at = c->log_head;
-    if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == at) v.extents.back().n += take;
-    else v.extents.push_back(Extent{at, take});
-    v.n_frames += take;
+    const uint64_t at = c->log_head, vpos = vbase + f;
+    if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == at && v.extents.back().vpos + v.extents.back().n == vpos)
+      v.extents.back().n += take;
+    else v.extents.push_back(Extent{at, take, vpos});
+    v.slab_epoch[c->cur] = s->epoch;
     c->log_head += take;
     s->frames += take;
     s->seg_recs += take_recs;
     s->bytes += nbytes;
+    const uint8_t* from = src + src_rec * in_stride;
     src_rec += take_recs;
     f += take;
-    if (s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes) {
+    const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
+    if (nbytes) {
+      s->writers.fetch_add(1, std::memory_order_relaxed);
+      if (staged)
+        for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
+          s->pend[k].fetch_add(1, std::memory_order_relaxed);
+      s->reserved_end.store(s->bytes, std::memory_order_release);
+      // ---- fill + commit outside the mutex -------------------------------------------------------------
+      const uint64_t my_epoch = s->epoch;
+      lk.unlock();
+      const int rc = fill_and_commit(c, *s, kind, off, nbytes, from, take_recs);
+      if (rc && !result) result = rc;
+      if (f >= n_frames && !slab_full) break;  // common case: done without taking the mutex again
+      lk.lock();
+      if (slab_full && &c->slabs[c->cur] == s && s->epoch == my_epoch) {
+        int rc2 = flush_locked(c);
+        if (rc2) return rc2;
+      }
+    } else if (slab_full) {
       int rc = flush_locked(c);
       if (rc) return rc;
     }
   }
-  return MSCAN_OK;
+  if (result == MSCAN_ERR_CUDA) {
+    if (!lk.owns_lock()) lk.lock();
+    return fail(c, result, "cudaMemcpyAsync of pinned caller records failed");
+  }
+  return result;
 } catch (...) {
   return on_exception(c);
 }
@@ -1148,8 +1387,7 @@ int mscan_set_staging_mode(mscan_ctx* c, int mode) {
 int mscan_set_pack_threads(mscan_ctx* c, int n_threads) try {
   if (!c || n_threads < 0) return MSCAN_ERR_INVALID;
   std::lock_guard<std::mutex> lk(c->mu);
-  c->pack_threads = n_threads;
-  c->pool.reset();  // re-created with the new size at the next large projection
+  c->pack_threads = n_threads;  // the pool itself is shared by every context of the process
   return MSCAN_OK;
 } catch (...) {
   return on_exception(c);
@@ -1168,21 +1406,24 @@ int mscan_flush(mscan_ctx* c) try {
 int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) try {
   ApiTimer trace_(c, "mscan_collect");
   if (!c) return MSCAN_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::unique_lock<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
-  const Video& v = it->second;
-  if (n_out) *n_out = (uint32_t)v.n_frames;
-  if (v.n_frames > cap && (flags || counts)) return fail(c, MSCAN_ERR_CAPACITY, "need room for %llu frames", (unsigned long long)v.n_frames);
-  int rc = sync_scans_locked(c);
+  if (n_out) *n_out = (uint32_t)it->second.n_frames;
+  if (it->second.n_frames > cap && (flags || counts))
+    return fail(c, MSCAN_ERR_CAPACITY, "need room for %llu frames", (unsigned long long)it->second.n_frames);
+  if (!flags && !counts) return MSCAN_OK;  // size query
+  int rc = sync_videos(c, lk, &video_id, 1);
   if (rc) return rc;
-  uint64_t at = 0;
+  it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during the call", video_id);
+  const Video& v = it->second;
   for (const Extent& e : v.extents) {
-    if (flags) CU(cudaMemcpyAsync(flags + at, c->d_flags + e.start, e.n, cudaMemcpyDeviceToHost, c->main_stream));
-    if (counts) CU(cudaMemcpyAsync(counts + at, c->d_counts + e.start, e.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
+    if (e.vpos + e.n > cap) return fail(c, MSCAN_ERR_CAPACITY, "need room for %llu frames", (unsigned long long)v.n_frames);
+    if (flags) CU(cudaMemcpyAsync(flags + e.vpos, c->d_flags + e.start, e.n, cudaMemcpyDeviceToHost, c->main_stream));
+    if (counts) CU(cudaMemcpyAsync(counts + e.vpos, c->d_counts + e.start, e.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
     c->stats.d2h_bytes += (flags ? e.n : 0) + (counts ? 4 * e.n : 0);
-    at += e.n;
   }
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;
@@ -1193,26 +1434,26 @@ int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* cou
 int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_t n, uint8_t* flags, uint32_t* counts) try {
   ApiTimer trace_(c, "mscan_collect_range");
   if (!c) return MSCAN_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::unique_lock<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
-  const Video& v = it->second;
-  if (first + n > v.n_frames) return fail(c, MSCAN_ERR_INVALID, "range [%llu,+%u) exceeds the video's %llu frames",
-                                          (unsigned long long)first, n, (unsigned long long)v.n_frames);
-  int rc = sync_scans_locked(c);
+  if (first + n > it->second.n_frames)
+    return fail(c, MSCAN_ERR_INVALID, "range [%llu,+%u) exceeds the video's %llu frames", (unsigned long long)first, n,
+                (unsigned long long)it->second.n_frames);
+  int rc = sync_videos(c, lk, &video_id, 1);
   if (rc) return rc;
-  uint64_t pos = 0, out = 0;  // pos: video-local index of the current extent's first frame
+  it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during the call", video_id);
+  const Video& v = it->second;
   for (const Extent& e : v.extents) {
-    const uint64_t a = std::max<uint64_t>(first, pos), b = std::min<uint64_t>(first + n, pos + e.n);
+    const uint64_t a = std::max<uint64_t>(first, e.vpos), b = std::min<uint64_t>(first + n, e.vpos + e.n);
     if (a < b) {
-      const uint64_t src = e.start + (a - pos), m = b - a;
+      const uint64_t src = e.start + (a - e.vpos), m = b - a, out = a - first;
       if (flags) CU(cudaMemcpyAsync(flags + out, c->d_flags + src, m, cudaMemcpyDeviceToHost, c->main_stream));
       if (counts) CU(cudaMemcpyAsync(counts + out, c->d_counts + src, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
       c->stats.d2h_bytes += (flags ? m : 0) + (counts ? 4 * m : 0);
-      out += m;
     }
-    pos += e.n;
   }
   CU(cudaStreamSynchronize(c->main_stream));
   return MSCAN_OK;
@@ -1220,10 +1461,13 @@ int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_
   return on_exception(c);
 }
 
-// Runs K-C for a list of open videos; leaves results in c->h_res and segments on the device.
-static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, const double* durations,
-                               std::vector<uint64_t>* seg_base_out) {
-  int rc = sync_scans_locked(c);
+// Runs K-C for a list of open videos; leaves results in c->h_res and segments on the device. Caller holds tail_mu
+// (K-C scratch, main_stream) and `lk` = mu; mu is released while the scans of these videos finish and while K-C runs.
+static int run_segments_locked(mscan_ctx* c, std::unique_lock<std::mutex>& lk, uint32_t n_videos, const uint32_t* ids,
+                               const double* durations, std::vector<uint64_t>* seg_base_out) {
+  for (uint32_t i = 0; i < n_videos; ++i)
+    if (!c->videos.count(ids[i])) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", ids[i]);
+  int rc = sync_videos(c, lk, ids, n_videos);
   if (rc) return rc;
   uint64_t n_ext = 0, ts_total = 0, seg_total = 0;
   for (uint32_t i = 0; i < n_videos; ++i) {
@@ -1269,11 +1513,15 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
   c->dev_jobs_cached.clear();
   seg_base_out->resize(n_videos);
   uint64_t e = 0, ts_at = 0, seg_at = 0;
+  std::vector<Extent> ordered;
   for (uint32_t i = 0; i < n_videos; ++i) {
     const Video& v = c->videos.find(ids[i])->second;
     SegJob j{};
     j.ext_begin = (uint32_t)e;
-    for (const Extent& x : v.extents) c->h_exts[e++] = SegExtent{x.start, x.n};
+    // in submission order: chunks that arrived in order then compact to an increasing list and K-C skips its sort
+    ordered = v.extents;
+    std::sort(ordered.begin(), ordered.end(), [](const Extent& x, const Extent& y) { return x.vpos < y.vpos; });
+    for (const Extent& x : ordered) c->h_exts[e++] = SegExtent{x.start, x.n};
     j.ext_end = (uint32_t)e;
     j.ts_base = ts_at;
     j.ts_cap = pow2_ge(std::max<uint64_t>(v.n_frames, 1));
@@ -1284,10 +1532,17 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
     seg_at += std::max<uint64_t>(v.n_frames, 1);
     c->h_jobs[i] = j;
   }
-  cudaStream_t st = c->main_stream;
-  CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice, st));
-  if (n_ext) CU(cudaMemcpyAsync(c->d_exts, c->h_exts, sizeof(SegExtent) * n_ext, cudaMemcpyHostToDevice, st));
+  const bool profiling = c->profiling;
+  EvPair ev{};
+  if (profiling) ev = get_events(c, 1);
   c->stats.h2d_bytes += sizeof(SegJob) * n_videos + sizeof(SegExtent) * n_ext;
+  c->stats.segment_launches += 1;
+  c->stats.d2h_bytes += sizeof(mscan_video_result) * n_videos;
+  // K-C reads the videos' (finished) frame-log extents and its own scratch: the bookkeeping mutex is not needed
+  lk.unlock();
+  cudaStream_t st = c->main_stream;
+  cudaError_t ce = cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(SegJob) * n_videos, cudaMemcpyHostToDevice, st);
+  if (ce == cudaSuccess && n_ext) ce = cudaMemcpyAsync(c->d_exts, c->h_exts, sizeof(SegExtent) * n_ext, cudaMemcpyHostToDevice, st);
   SegArgs a{};
   a.jobs = c->d_jobs;
   a.extents = c->d_exts;
@@ -1300,20 +1555,14 @@ static int run_segments_locked(mscan_ctx* c, uint32_t n_videos, const uint32_t* 
   a.max_gap = c->params.max_gap_sec;
   a.padding = c->params.padding_sec;
   a.min_savings_pct = c->params.min_savings_pct;
-  EvPair ev{};
-  if (c->profiling) {
-    ev = get_events(c, 1);
-    cudaEventRecord(ev.a, st);
-  }
-  CU(segments_launch(a, n_videos, st));
-  if (c->profiling) {
-    cudaEventRecord(ev.b, st);
-    c->ev_pending.push_back(ev);
-  }
-  c->stats.segment_launches += 1;
-  CU(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(mscan_video_result) * n_videos, cudaMemcpyDeviceToHost, st));
-  c->stats.d2h_bytes += sizeof(mscan_video_result) * n_videos;
-  CU(cudaStreamSynchronize(st));
+  if (profiling) cudaEventRecord(ev.a, st);
+  if (ce == cudaSuccess) ce = segments_launch(a, n_videos, st);
+  if (profiling) cudaEventRecord(ev.b, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(c->h_res, c->d_res, sizeof(mscan_video_result) * n_videos, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  lk.lock();
+  if (profiling) c->ev_pending.push_back(ev);
+  if (ce != cudaSuccess) return fail(c, MSCAN_ERR_CUDA, "K-C launch failed: %s", cudaGetErrorString(ce));
   return MSCAN_OK;
 }
 
@@ -1322,14 +1571,15 @@ static int segments_impl(mscan_ctx* c, uint32_t n_videos, const uint32_t* ids, c
                          bool job_semantics) try {
   ApiTimer trace_(c, "mscan_segments[_batch]");
   if (!c || (n_videos && (!ids || !durations))) return MSCAN_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(c->mu);
+  std::lock_guard<std::mutex> tail(c->tail_mu);
+  std::unique_lock<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   if (n_videos == 0) {
     if (seg_off_out) seg_off_out[0] = 0;
     return MSCAN_OK;
   }
   std::vector<uint64_t> seg_base;
-  int rc = run_segments_locked(c, n_videos, ids, durations, &seg_base);
+  int rc = run_segments_locked(c, lk, n_videos, ids, durations, &seg_base);
   if (rc) return rc;
   uint64_t at = 0;
   bool overflow = false;
@@ -1383,13 +1633,15 @@ int mscan_motion_segments(mscan_ctx* c, uint32_t video_id, double duration, msca
 int mscan_video_close(mscan_ctx* c, uint32_t video_id) try {
   ApiTimer trace_(c, "mscan_video_close");
   if (!c) return MSCAN_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(c->mu);
-  auto it = c->videos.find(video_id);
-  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
-  // the video's log frames become reusable: no scan in flight may still write them
+  std::unique_lock<std::mutex> lk(c->mu);
+  if (!c->videos.count(video_id)) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  // the video's log frames become reusable: no scan in flight may still write them (only this video's scans are
+  // waited for — the other streams of the GPU keep running)
   CU(cudaSetDevice(c->device));
-  int rc = sync_scans_locked(c);
+  int rc = sync_videos(c, lk, &video_id, 1);
   if (rc) return rc;
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return MSCAN_OK;  // closed by another thread while we waited
   c->videos.erase(it);
   if (c->videos.empty()) {  // nothing live any more: rewind
     c->log_head = 0;
@@ -1438,6 +1690,8 @@ int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, 
     if (rc) return rc;
   }
   const std::vector<Extent> src_extents = sv.extents;  // dst == src: dv.extents grows below
+  const uint64_t dv_base = dv.n_frames;                 // the adopted frames keep their order behind the video's own
+  const uint64_t sv_frames = sv.n_frames;
   uint64_t done_frames = 0;
   for (const Extent& e : src_extents) {
     uint64_t off = 0;
@@ -1450,14 +1704,16 @@ int mscan_video_append_from(mscan_ctx* dst, uint32_t dst_video, mscan_ctx* src, 
       CU(cudaMemcpyPeerAsync(dst->d_pts + at, dst->device, src->d_pts + from, src->device, sizeof(double) * m, dst->main_stream));
       CU(cudaMemcpyPeerAsync(dst->d_flags + at, dst->device, src->d_flags + from, src->device, m, dst->main_stream));
       CU(cudaMemcpyPeerAsync(dst->d_counts + at, dst->device, src->d_counts + from, src->device, sizeof(uint32_t) * m, dst->main_stream));
-      if (!dv.extents.empty() && dv.extents.back().start + dv.extents.back().n == at) dv.extents.back().n += m;
-      else dv.extents.push_back(Extent{at, m});
-      dv.n_frames += m;
+      const uint64_t vpos = dv_base + e.vpos + off;
+      if (!dv.extents.empty() && dv.extents.back().start + dv.extents.back().n == at && dv.extents.back().vpos + dv.extents.back().n == vpos)
+        dv.extents.back().n += m;
+      else dv.extents.push_back(Extent{at, m, vpos});
       dst->log_head += m;
       off += m;
       done_frames += m;
     }
   }
+  dv.n_frames = dv_base + sv_frames;
   CU(cudaStreamSynchronize(dst->main_stream));
   dst->stats.peer_bytes += 13ull * done_frames;
   return MSCAN_OK;
@@ -1472,12 +1728,16 @@ int mscan_host_alloc(mscan_ctx* c, size_t bytes, void** p) {
     cudaGetLastError();
     return fail(c, MSCAN_ERR_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
   }
+  pinned_ranges().add(*p, bytes ? bytes : 1);
   return MSCAN_OK;
 }
 
 int mscan_host_free(mscan_ctx* c, void* p) {
   if (!c) return MSCAN_ERR_INVALID;
-  if (p) CU(cudaFreeHost(p));
+  if (p) {
+    pinned_ranges().remove(p);
+    CU(cudaFreeHost(p));
+  }
   return MSCAN_OK;
 }
 
@@ -1493,12 +1753,14 @@ int mscan_host_register(mscan_ctx* c, void* p, size_t bytes, int read_only) {
     return fail(c, MSCAN_ERR_CUDA, "cudaHostRegister(%zu bytes%s) refused: %s", bytes, read_only ? ", read-only" : "",
                 cudaGetErrorString(e));
   }
+  pinned_ranges().add(p, bytes);
   return MSCAN_OK;
 }
 
 int mscan_host_unregister(mscan_ctx* c, void* p) {
   if (!c || !p) return MSCAN_ERR_INVALID;
   CU(cudaSetDevice(c->device));
+  pinned_ranges().remove(p);
   CU(cudaHostUnregister(p));
   return MSCAN_OK;
 }
@@ -1640,6 +1902,7 @@ int mscan_segments_device(mscan_ctx* c, uint32_t n_videos, const uint64_t* h_vid
                           mscan_video_result* d_results, void* stream) try {
   if (!c || !h_video_off || !h_durations || !d_pts || !d_flags || !d_segments || !d_results) return MSCAN_ERR_INVALID;
   if (n_videos == 0) return MSCAN_OK;
+  std::lock_guard<std::mutex> tail(c->tail_mu);  // K-C scratch is shared with mscan_segments*
   std::lock_guard<std::mutex> lk(c->mu);
   CU(cudaSetDevice(c->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : c->main_stream;

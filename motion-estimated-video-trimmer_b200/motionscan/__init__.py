@@ -104,6 +104,8 @@ class MvgenSpec(C.Structure):
         ("static_b0", C.c_int32),
         ("static_b1", C.c_int32),
         ("fps", C.c_double),
+        ("scatter", C.c_int32),
+        ("p_rec_move", C.c_uint32),
     ]
 
 
@@ -476,3 +478,105 @@ class Context:
 
     def set_profiling(self, on: bool):
         self._ck(self.L.mscan_set_profiling(self.h, int(on)))
+
+
+# ---- measurement harness: decode-worker stand-in threads (csrc/feed_harness.cpp → libmscan_feed.so) -------------
+FEED_LIB_PATH = PKG_DIR / "libmscan_feed.so"
+
+
+class FeedSpec(C.Structure):
+    _fields_ = [
+        ("n_threads", C.c_int32),
+        ("cpus", C.c_void_p),
+        ("n_videos", C.c_uint32),
+        ("video_ids", C.c_void_p),
+        ("video_frame_off", C.c_void_p),
+        ("pts", C.c_void_p),
+        ("rec_count", C.c_void_p),
+        ("rec_off", C.c_void_p),
+        ("source", C.c_void_p),
+        ("source_kind", C.c_int32),
+        ("frames_per_submit", C.c_uint32),
+        ("submit_kind", C.c_int32),
+        ("frame_index_out", C.c_void_p),
+    ]
+
+
+class FeedResult(C.Structure):
+    _fields_ = [
+        ("wall_s", C.c_double),
+        ("hot_max_s", C.c_double),
+        ("hot_sum_s", C.c_double),
+        ("standin_max_s", C.c_double),
+        ("standin_sum_s", C.c_double),
+        ("frames", C.c_uint64),
+        ("records", C.c_uint64),
+        ("submits", C.c_uint64),
+        ("rc", C.c_int32),
+        ("avx512", C.c_int32),
+    ]
+
+
+_feed = None
+
+
+def feed_lib() -> C.CDLL:
+    global _feed
+    if _feed is None:
+        lib()  # libmotionscan.so first: the harness links against it
+        if not FEED_LIB_PATH.exists():
+            raise FileNotFoundError(f"{FEED_LIB_PATH} is missing — build it with `python {PKG_DIR.name}/build.py`")
+        L = C.CDLL(str(FEED_LIB_PATH))
+        L.mscan_feed_run.restype = C.c_int
+        L.mscan_feed_run.argtypes = [C.c_void_p, C.POINTER(FeedSpec), C.POINTER(FeedResult)]
+        L.mscan_feed_expand.restype = C.c_int
+        L.mscan_feed_expand.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        _feed = L
+    return _feed
+
+
+def feed_expand(recs8: np.ndarray) -> np.ndarray:
+    """The stand-in decoder's record writer: native records (MV_DTYPE) from MV8_DTYPE coordinates."""
+    assert recs8.dtype == MV8_DTYPE and recs8.flags["C_CONTIGUOUS"]
+    out = np.zeros(len(recs8), dtype=MV_DTYPE)
+    rc = feed_lib().mscan_feed_expand(_ptr(recs8), len(recs8), _ptr(out))
+    if rc:
+        raise MscanError(rc, "mscan_feed_expand")
+    return out
+
+
+def feed_run(ctx: "Context", video_ids, video_frame_off, pts, rec_count, rec_off, source, *, n_threads: int, cpus=None,
+             frames_per_submit: int = 1, submit_kind: int = 0, want_index: bool = True):
+    """T decode-worker stand-ins feed `ctx` (see csrc/feed_harness.cpp). `source`: MV8_DTYPE (expanded to native
+    records per frame by the stand-in) or MV_DTYPE (copied). Returns (FeedResult, frame_index or None)."""
+    video_ids = np.ascontiguousarray(video_ids, dtype=np.uint32)
+    video_frame_off = np.ascontiguousarray(video_frame_off, dtype=np.uint64)
+    rec_count = np.ascontiguousarray(rec_count, dtype=np.uint32)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    assert source.dtype in (MV8_DTYPE, MV_DTYPE) and source.flags["C_CONTIGUOUS"]
+    n_frames = int(video_frame_off[-1])
+    assert len(pts) >= n_frames and len(rec_count) >= n_frames and len(rec_off) >= n_frames + 1
+    cpu_arr = np.ascontiguousarray(cpus, dtype=np.int32) if cpus is not None else None
+    assert cpu_arr is None or len(cpu_arr) >= n_threads
+    index = np.zeros(n_frames, dtype=np.uint64) if want_index else None
+    sp = FeedSpec(
+        n_threads=n_threads,
+        cpus=_ptr(cpu_arr),
+        n_videos=len(video_ids),
+        video_ids=_ptr(video_ids),
+        video_frame_off=_ptr(video_frame_off),
+        pts=_ptr(pts),
+        rec_count=_ptr(rec_count),
+        rec_off=_ptr(rec_off),
+        source=_ptr(source),
+        source_kind=1 if source.dtype == MV8_DTYPE else 0,
+        frames_per_submit=frames_per_submit,
+        submit_kind=submit_kind,
+        frame_index_out=_ptr(index),
+    )
+    res = FeedResult()
+    rc = feed_lib().mscan_feed_run(ctx.h, C.byref(sp), C.byref(res))
+    if rc:
+        raise MscanError(rc, ctx.L.mscan_last_error(ctx.h).decode())
+    return res, index

@@ -20,7 +20,7 @@ ROOT = Path(__file__).resolve().parent.parent.parent
 sys.path[:0] = [str(ROOT / "motion-estimated-video-trimmer_b200"), str(ROOT / "tests")]
 
 import golden_cases as gc  # noqa: E402
-import mvs_io  # noqa: E402
+from motionscan import mvs_io  # noqa: E402
 import ref_runner  # noqa: E402
 
 

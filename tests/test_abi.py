@@ -35,7 +35,7 @@ def test_struct_layouts():
     assert C.sizeof(ms.VideoResult) == 40 and ms.RESULT_DTYPE.itemsize == 40
     assert C.sizeof(ms.Stats) == 96
     assert ms.MV8_DTYPE.itemsize == 8
-    assert C.sizeof(ms.MvgenSpec) == 88
+    assert C.sizeof(ms.MvgenSpec) == 96  # + scatter, p_rec_move (SURVEY §8(d) config-5 shape)
 
 
 def test_defaults_and_env(monkeypatch):
@@ -133,3 +133,37 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.split()[:2] == ["40", "8"]
+
+
+def test_feed_harness_standin_writes_full_native_records():
+    """The decode stand-in of the measurement harness (csrc/feed_harness.cpp) expands 8-byte coordinates into complete
+    40-byte AVMotionVector records — byte-identical to the generator's own records — with and without AVX-512."""
+    spec = ms.synth_preset(4, 5)
+    cnt, off, recs, pts = ms.synth_host(spec, 1, 3)
+    r8 = ms.pack_records(recs)
+    ex = ms.feed_expand(r8)
+    for f in ("source", "src_x", "src_y", "dst_x", "dst_y", "flags", "motion_x", "motion_y", "motion_scale"):
+        assert np.array_equal(ex[f], recs[f]), f
+    assert ms.pack_records(ex).tobytes() == r8.tobytes()
+    assert hasattr(ms.feed_lib(), "mscan_feed_run")
+
+
+def test_generator_library_alone_matches_and_spec_stream_shape():
+    """libmvgen.so (what bench.py --impl reference loads instead of the product library) generates the same bytes;
+    preset 5 is SURVEY §8(d) config 5 as specified: 16 320 records per 1080p frame, ~10 % moving, ~0.1 % out of frame."""
+    from motionscan import mvgen
+
+    for preset in (0, 4, 5):
+        a = ms.synth_host(ms.synth_preset(preset, 9), 3, 6)
+        b = mvgen.synth_host(mvgen.synth_preset(preset, 9), 3, 6)
+        assert a[2].tobytes() == b[2].tobytes() and np.array_equal(a[0], b[0]) and np.array_equal(a[3], b[3])
+    cnt, off, recs, pts = mvgen.synth_host(mvgen.synth_preset(5, 5), 0, 40)
+    assert (cnt == 16320).all()
+    moving = (recs["src_x"] != recs["dst_x"]) | (recs["src_y"] != recs["dst_y"])
+    assert 0.09 < moving.mean() < 0.11
+    d = np.stack([recs["dst_x"].astype(int) - recs["src_x"], recs["dst_y"].astype(int) - recs["src_y"]])
+    assert d.min() == -8 and d.max() == 8
+    oob = (recs["dst_x"] < 0) | (recs["dst_x"] >= 1920) | (recs["dst_y"] < 0) | (recs["dst_y"] >= 1088)
+    assert 0.0003 < oob.mean() < 0.003
+    # uniform dst: consecutive records are NOT raster-ordered
+    assert (np.diff(recs["dst_y"][:1000].astype(int)) < 0).mean() > 0.3

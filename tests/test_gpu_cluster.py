@@ -153,3 +153,64 @@ with ms.Context(0, p) as ctx:
     for v, (w, h) in shapes.items():
         cfg, *_ = cfg_for(p, w, h)
         assert got[str(v)][0] == [orc.full_count(cfg, f) for f in frames[v]], v
+
+
+@pytest.mark.parametrize("big,small", [("16k", (320, 240)), ("8k", (320, 64)), ("16k", (1920, 64)), ("strip", (640, 480))])
+@pytest.mark.parametrize("mode", ["native", "projected"])
+def test_tiny_grid_shares_a_context_with_a_cluster_sized_one(big, small, mode):
+    """A video whose grid has no more rows than the cluster has CTAs (one row per band, or bands without rows) in the
+    same context — and the same launches — as a grid that needs the cluster: every vote must reach the band that owns
+    its row, and the frames after the small video's must not see leftovers (the cluster size is chosen per context
+    from the largest geometry, so the small grid runs with rows-per-band == 1)."""
+    bw, bh = SHAPES[big]
+    sw, sh = small
+    rng = np.random.default_rng(hash((big, small)) % 100000)
+    p = kats.env_params(vectors_needed=2, clusters_needed=1, vertical_mask=0.26)  # margin >= 1 also for 4-row grids
+    cfg_b, *_ = cfg_for(p, bw, bh)
+    cfg_s, gws, ghs, ms_ = cfg_for(p, sw, sh)
+    assert ms_ >= 1
+    small_frames, big_frames = [], []
+    for i in range(10):
+        f = random_frame(rng, int(rng.integers(50, 3000)), sw, sh, int(rng.integers(1, 4)))
+        # make sure live rows beyond row 0 get clusters: stack heavy neighbouring cells in every live row
+        rows = range(ms_, ghs - ms_)
+        f = kats.cat(f, *[kats.cell(1 + (i % max(gws - 3, 1)), y, 6) for y in rows], *[kats.cell(2 + (i % max(gws - 3, 1)), y, 6) for y in rows])
+        small_frames.append(f)
+        big_frames.append(random_frame(rng, int(rng.integers(1, 20000)), bw, bh, int(rng.integers(2, 8))))
+    with ms.Context(0, p) as ctx:
+        ctx.set_staging_mode(ms.STAGING_NATIVE if mode == "native" else ms.STAGING_AUTO)
+        ctx.video_open(1, bw, bh)
+        ctx.video_open(2, sw, sh)
+        for i in range(10):  # interleaved: small frame, then a big one in the same segment
+            ctx.submit(2, np.array([i / 30.0]), np.array([len(small_frames[i])], np.uint32), small_frames[i])
+            ctx.submit(1, np.array([i / 30.0]), np.array([len(big_frames[i])], np.uint32), big_frames[i])
+        fs, cs = ctx.collect(2)
+        fb, cb = ctx.collect(1)
+    want_s = [orc.full_count(cfg_s, f) for f in small_frames]
+    want_b = [orc.full_count(cfg_b, f) for f in big_frames]
+    assert max(want_s) > 0
+    assert list(cs) == want_s, (big, small, mode)
+    assert list(cb) == want_b, (big, small, mode)
+    assert list(fs) == [orc.check_frame(cfg_s, f) for f in small_frames]
+
+
+def test_remote_votes_saturate_without_carry_16k():
+    """Many votes into ONE cell owned by another CTA of the cluster (red.shared::cluster with the carry guard), from a
+    frame whose records are shuffled so that every CTA's slice votes remotely: the 16-bit half must not carry into its
+    word-mate — the neighbouring cell stays inactive."""
+    w, h = SHAPES["16k"]
+    p = kats.env_params(vectors_needed=200, clusters_needed=1)
+    cfg, gw, gh, m = cfg_for(p, w, h)
+    gx, gy = 200, gh - m - 2                      # a cell of the last bands
+    gx -= gx & 1                                  # even x: its word-mate is (gx+1, gy)
+    heavy = kats.cell(gx, gy, 150000)
+    mate_light = kats.cell(gx + 1, gy, 150)       # below VECTORS_NEEDED: must stay inactive whatever the left half does
+    other = kats.cat(kats.cell(50, m + 1, 300), kats.cell(51, m + 1, 300))  # one real cluster pair elsewhere
+    rng = np.random.default_rng(5)
+    f = kats.cat(heavy, mate_light, other)
+    f = f[rng.permutation(len(f))]
+    want = orc.full_count(cfg, f)
+    assert want == 2
+    for mode in ("native", "projected"):
+        flags, counts = scan(p, w, h, [f, kats.cell(gx + 1, gy, 150), f], mode)
+        assert list(counts) == [want, 0, want], mode

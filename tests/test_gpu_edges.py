@@ -1,5 +1,6 @@
 """GPU: edge cases and size-independent properties — degenerate knobs, empty inputs, concurrent submits,
 idempotence / batching invariance at a large device-resident size with oracle spot checks."""
+import os
 import threading
 import zlib
 
@@ -105,6 +106,75 @@ def test_concurrent_submits_from_many_threads():
         assert res["decision"][i] == ores.decision and res["n_motion_frames"][i] == ores.n_motion_frames
         assert motion[v][0].tobytes() == osegs.tobytes()
         assert np.float64(res["saved_pct"][i]).tobytes() == np.float64(ores.saved_pct).tobytes()
+
+
+@pytest.mark.parametrize("n_threads,batch", [(16, 1), (24, 3), (5, 1)])
+def test_decode_worker_standins_submit_per_frame(n_threads, batch):
+    """16+ decode-worker stand-ins (csrc/feed_harness.cpp) each write their frames' native records into a private,
+    pageable side-data buffer and call mscan_submit PER FRAME, concurrently, on shared videos: the reserve / fill /
+    commit submit must give every frame exactly the oracle's result, whatever the interleaving. Small slabs and copy
+    windows so that slabs flip, windows close and videos wrap many times."""
+    p = kats.env_params()
+    specs = [ms.synth_preset(0, 300 + v) for v in range(3)]
+    data = [ms.synth_host(s, 0, 360) for s in specs]
+    cnt = np.concatenate([d[0] for d in data])
+    pts = np.concatenate([d[3] for d in data])
+    recs = kats.cat(*[d[2] for d in data])
+    off = np.zeros(len(cnt) + 1, np.uint64)
+    np.cumsum(cnt, out=off[1:])
+    voff = np.array([0, 360, 720, 1080], np.uint64)
+    r8 = ms.pack_records(recs)
+    cfg = cfg_for(p, 1920, 1080)
+    of, oc = orc.scan_frames(cfg, recs, off, threads=4)
+    os.environ["MSCAN_COPY_WINDOW_KB"] = "256"
+    try:
+        with ms.Context(0, p, 0, 4 << 20) as ctx:
+            for rep in range(3):
+                for v in range(3):
+                    ctx.video_open(v, 1920, 1080)
+                res, index = ms.feed_run(ctx, [0, 1, 2], voff, pts, cnt, off, r8, n_threads=n_threads, frames_per_submit=batch)
+                assert res.records == int(off[-1]) and res.frames == 1080 and res.submits >= 1080 // batch
+                segs, soff, vres = ctx.segments_batch([0, 1, 2], [12.0] * 3)
+                for v in range(3):
+                    a, b = int(voff[v]), int(voff[v + 1])
+                    fl, cn = ctx.collect(v)
+                    idx = index[a:b].astype(np.int64)
+                    assert sorted(idx.tolist()) == list(range(b - a))        # every frame got its own slot
+                    assert np.array_equal(fl[idx], of[a:b]) and np.array_equal(cn[idx], oc[a:b]), (rep, v)
+                    osegs, ores = oracle_tail(p, pts[a:b], of[a:b], 12.0)
+                    assert vres["decision"][v] == ores.decision and vres["n_motion_frames"][v] == ores.n_motion_frames
+                    job = segs[int(soff[v]) : int(soff[v + 1])]
+                    if ores.decision == ms.CUT:
+                        assert job.tobytes() == osegs.tobytes()
+                    ctx.video_close(v)
+            st = ctx.stats()
+            assert st.records_projected == 3 * int(off[-1])  # pageable native records: projected by the submitting threads
+    finally:
+        del os.environ["MSCAN_COPY_WINDOW_KB"]
+
+
+def test_video_tail_does_not_drain_other_videos():
+    """collect / segments / close of one video wait only for the slabs holding ITS frames: a second video with a large
+    pinned submit in flight is not drained by the first video's tail (its results are still correct afterwards)."""
+    p = kats.env_params()
+    sa, sb = ms.synth_preset(0, 410), ms.synth_preset(0, 411)
+    a = ms.synth_host(sa, 0, 60)
+    b = ms.synth_host(sb, 0, 900)
+    cfg = cfg_for(p, 1920, 1080)
+    with ms.Context(0, p, 0, 8 << 20) as ctx:
+        ctx.video_open(1, 1920, 1080)
+        ctx.video_open(2, 1920, 1080)
+        for rep in range(4):
+            ctx.submit(1, a[3], a[0], a[2])
+            ctx.submit(2, b[3] + 30.0 * rep, b[0], b[2])
+            fl, cn = ctx.collect_range(1, 60 * rep, 60)
+            of, oc = orc.scan_frames(cfg, a[2], a[1])
+            assert np.array_equal(fl, of) and np.array_equal(cn, oc)
+        fl2, cn2 = ctx.collect(2)
+        of2, oc2 = orc.scan_frames(cfg, b[2], b[1], threads=4)
+        assert np.array_equal(fl2, np.tile(of2, 4)) and np.array_equal(cn2, np.tile(oc2, 4))
+        ctx.video_close(1)
+        ctx.video_close(2)
 
 
 def test_fullsize_properties_device_resident():

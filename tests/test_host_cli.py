@@ -10,7 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-import mvs_io
+from motionscan import mvs_io
 import ref_runner
 from test_ref_golden import GOLDEN, cases, expected
 

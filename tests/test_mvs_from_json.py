@@ -10,7 +10,7 @@ import numpy as np
 
 import kats
 import motionscan as ms
-import mvs_io
+from motionscan import mvs_io
 import oracle_lib as orc
 
 ROOT = Path(__file__).resolve().parent.parent

@@ -11,7 +11,7 @@ import pytest
 
 import golden_cases as gc
 import kats
-import mvs_io
+from motionscan import mvs_io
 import oracle_lib as orc
 import ref_runner
 

@@ -24,7 +24,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT / "motion-estimated-video-trimmer_b200"), str(ROOT / "tests")]
 import motionscan as ms  # noqa: E402
-import mvs_io  # noqa: E402
+from motionscan import mvs_io  # noqa: E402
 
 BIN = ROOT / "motion-estimated-video-trimmer_b200" / "host" / "motion_trim_b200"
 

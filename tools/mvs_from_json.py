@@ -21,7 +21,7 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
-sys.path[:0] = [str(ROOT / "motion-estimated-video-trimmer_b200"), str(ROOT / "tests")]
+sys.path[:0] = [str(ROOT / "motion-estimated-video-trimmer_b200")]
 
 
 def c_div(a: int, b: int) -> int:
@@ -67,7 +67,7 @@ def convert(doc: dict, width: int, height: int, fps: Fraction | None = None):
 
 
 def main():
-    import mvs_io
+    from motionscan import mvs_io
 
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("json")
