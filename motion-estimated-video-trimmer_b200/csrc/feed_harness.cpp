@@ -43,7 +43,9 @@ typedef struct mscan_feed_spec {
   const void* source;             /* decoder stand-in input: mscan_mv8[N] (source_kind 1) or mscan_mv[N] (0) */
   int32_t source_kind;
   uint32_t frames_per_submit;     /* 1 = one call per frame, like check_frame(frame)                      */
-  int32_t submit_kind;            /* 0: mscan_submit(native records); 1: mscan_pack_records + mscan_submit_packed */
+  int32_t submit_kind;            /* 0: mscan_submit(native records); 1: mscan_pack_records + mscan_submit_packed;
+                                     diagnosis only: 2 = stand-in alone (no call), 3 = stand-in + mscan_pack_records into a
+                                     private buffer (no submit) */
   uint64_t* frame_index_out;      /* [F] index of every frame in its video's submission order, or NULL    */
 } mscan_feed_spec;
 
@@ -211,8 +213,8 @@ extern "C" int mscan_feed_run(mscan_ctx* ctx, const mscan_feed_spec* sp, mscan_f
       // the decoder-owned side-data buffer (pageable, reused for every batch → stays in this core's cache)
       const size_t cap = (size_t)max_frame * batch;
       mscan_mv* sd = static_cast<mscan_mv*>(std::aligned_alloc(64, std::max<size_t>(64, (cap * sizeof(mscan_mv) + 127) & ~size_t(63))));
-      mscan_mv8* packed = sp->submit_kind == 1 ? static_cast<mscan_mv8*>(std::aligned_alloc(64, std::max<size_t>(64, (cap * 8 + 63) & ~size_t(63)))) : nullptr;
-      if (!sd || (sp->submit_kind == 1 && !packed)) r.rc = MSCAN_ERR_NOMEM;
+      mscan_mv8* packed = (sp->submit_kind == 1 || sp->submit_kind == 3) ? static_cast<mscan_mv8*>(std::aligned_alloc(64, std::max<size_t>(64, (cap * 8 + 63) & ~size_t(63)))) : nullptr;
+      if (!sd || ((sp->submit_kind == 1 || sp->submit_kind == 3) && !packed)) r.rc = MSCAN_ERR_NOMEM;
       if (sd) std::memset(sd, 0, cap * sizeof(mscan_mv));
       ready.fetch_add(1);
       while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
@@ -237,6 +239,10 @@ extern "C" int mscan_feed_run(mscan_ctx* ctx, const mscan_feed_spec* sp, mscan_f
         if (sp->submit_kind == 1) {
           rc = mscan_pack_records(sd, nrec, packed);
           if (rc == MSCAN_OK) rc = mscan_submit_packed(ctx, sp->video_ids[v], (uint32_t)(e - f), sp->pts + f, sp->rec_count + f, packed, &first);
+        } else if (sp->submit_kind == 2) {
+          rc = MSCAN_OK;
+        } else if (sp->submit_kind == 3) {
+          rc = mscan_pack_records(sd, nrec, packed);
         } else {
           rc = mscan_submit(ctx, sp->video_ids[v], (uint32_t)(e - f), sp->pts + f, sp->rec_count + f, sd, &first);
         }

@@ -232,27 +232,50 @@ class PinnedRanges {
   void add(const void* p, size_t n) {
     std::unique_lock<std::shared_mutex> lk(mu_);
     r_[reinterpret_cast<uintptr_t>(p)] = n;
-    count_.store(r_.size(), std::memory_order_release);
+    gen_.fetch_add(1, std::memory_order_release);
   }
   void remove(const void* p) {
     std::unique_lock<std::shared_mutex> lk(mu_);
     r_.erase(reinterpret_cast<uintptr_t>(p));
-    count_.store(r_.size(), std::memory_order_release);
+    gen_.fetch_add(1, std::memory_order_release);
   }
+  // Is [p, p+n) inside one registered range? Each thread remembers the last interval it asked about (a registered
+  // range, or the gap between two of them) together with the registry's generation, so a decode thread that submits
+  // from the same side-data buffer frame after frame never touches the shared lock.
   bool contains(const void* p, size_t n) {
-    if (count_.load(std::memory_order_acquire) == 0) return false;
-    std::shared_lock<std::shared_mutex> lk(mu_);
+    struct Last {
+      uint64_t gen = ~0ull;
+      uintptr_t lo = 0, hi = 0;
+      bool pinned = false;
+    };
+    static thread_local Last last;
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    auto it = r_.upper_bound(a);
-    if (it == r_.begin()) return false;
-    --it;
-    return a >= it->first && a + n <= it->first + it->second;
+    const uint64_t g = gen_.load(std::memory_order_acquire);
+    if (last.gen == g && a >= last.lo && a + n <= last.hi) return last.pinned;
+    std::shared_lock<std::shared_mutex> lk(mu_);
+    Last now;
+    now.gen = gen_.load(std::memory_order_acquire);
+    auto it = r_.upper_bound(a);  // first range starting above a
+    now.hi = it == r_.end() ? ~uintptr_t(0) : it->first;
+    if (it != r_.begin()) {
+      --it;
+      if (a < it->first + it->second) {  // a lies inside this range
+        now.lo = it->first;
+        now.hi = it->first + it->second;
+        now.pinned = true;
+      } else {
+        now.lo = it->first + it->second;
+      }
+    }
+    const bool inside = a + n <= now.hi;
+    if (inside || !now.pinned) last = now;  // (a request straddling the end of a range is simply not cached)
+    return now.pinned && inside;
   }
 
  private:
   std::shared_mutex mu_;
   std::map<uintptr_t, size_t> r_;
-  std::atomic<size_t> count_{0};
+  std::atomic<uint64_t> gen_{0};
 };
 PinnedRanges& pinned_ranges() {
   static PinnedRanges* r = new PinnedRanges();
@@ -543,6 +566,27 @@ ScanArgs base_args(mscan_ctx* c) {
   return a;
 }
 
+// Takes `mu` for a short critical section: spins briefly before blocking. With one lock acquisition per submitted frame
+// from every decode thread, a contended std::mutex::lock() puts the loser to sleep in the kernel, and the wake-up costs far
+// more (tens of µs in a VM) than the few hundred ns the holder needs.
+void lock_briefly(std::unique_lock<std::mutex>& lk) {
+  for (int spin = 0; spin < 2000; ++spin) {
+    if (lk.try_lock()) return;
+#if defined(__x86_64__)
+    _mm_pause();
+#endif
+  }
+  lk.lock();
+}
+
+// CUDA calls need the context's device current in the calling thread; the submit fast path (reserve / project / commit)
+// makes none, so this is only paid where something is enqueued.
+inline cudaError_t use_device(mscan_ctx* c) {
+  int d = -1;
+  if (cudaGetDevice(&d) == cudaSuccess && d == c->device) return cudaSuccess;
+  return cudaSetDevice(c->device);
+}
+
 // Copy pump (caller holds issue_mu): enqueues the H2D copy of every staged window of the open segment that is
 // complete — closed (the reservation pointer has moved past its end) and without uncommitted writers. Windows go out
 // in order, so copy_head is the only state; `seal` also sends the partial last window (launch_segment has already
@@ -565,7 +609,7 @@ int pump_locked(mscan_ctx* c, Slab& s, bool seal) {
 void try_pump(mscan_ctx* c, Slab& s) {
   std::unique_lock<std::mutex> lk(c->issue_mu, std::try_to_lock);
   if (!lk.owns_lock()) return;  // somebody is pumping or launching; launch_segment is the backstop
-  if (cudaSetDevice(c->device) != cudaSuccess) return;
+  if (use_device(c) != cudaSuccess) return;
   pump_locked(c, s, false);
 }
 
@@ -586,6 +630,7 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   if (n == 0) return MSCAN_OK;
   wait_writers(s);  // fills run outside mu and never need it to commit: this wait is bounded by one frame's projection
   std::lock_guard<std::mutex> issue(c->issue_mu);
+  CU(use_device(c));
   int rc = pump_locked(c, s, true);
   if (rc) return rc;
   s.h_rec_off[s.seg_slot0 + n] = s.seg_recs;
@@ -639,6 +684,7 @@ void recycle_slab(mscan_ctx* c, Slab& s) {
 
 int wait_slab(mscan_ctx* c, Slab& s) {
   if (s.in_flight) {
+    CU(use_device(c));
     CU(cudaEventSynchronize(s.done));
     s.in_flight = false;
   }
@@ -1166,7 +1212,7 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
     std::memcpy(s.h_recs + off, from, nbytes);
   } else if (kind == kFillInPlace) {
     std::lock_guard<std::mutex> issue(c->issue_mu);
-    cudaError_t e = cudaSetDevice(c->device);
+    cudaError_t e = use_device(c);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_recs + off, from, nbytes, cudaMemcpyHostToDevice, s.stream);
     if (e != cudaSuccess) rc = MSCAN_ERR_CUDA;
     c->a_h2d_bytes.fetch_add(nbytes, std::memory_order_relaxed);
@@ -1213,8 +1259,8 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       if (!pinned && src_bytes >= kAttrQueryBytes) pinned = is_pinned(recs);
     }
   }
-  std::unique_lock<std::mutex> lk(c->mu);
-  CU(cudaSetDevice(c->device));
+  std::unique_lock<std::mutex> lk(c->mu, std::defer_lock);
+  lock_briefly(lk);
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
   const uint64_t vbase = it->second.n_frames;  // this call owns video-local indices [vbase, vbase + n_frames)
@@ -1301,7 +1347,10 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       s->staged = staged;
       s->copy_head = s->seg_byte0;
     }
-    if (staged && nbytes && !s->h_recs) CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
+    if (staged && nbytes && !s->h_recs) {
+      CU(use_device(c));
+      CU(cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault));
+    }
     // ---- reserve: byte range, frame slots, log range --------------------------------------------------
     const uint64_t off = s->bytes;
     uint64_t r = s->seg_recs;
@@ -1338,7 +1387,7 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       const int rc = fill_and_commit(c, *s, kind, off, nbytes, from, take_recs);
       if (rc && !result) result = rc;
       if (f >= n_frames && !slab_full) break;  // common case: done without taking the mutex again
-      lk.lock();
+      lock_briefly(lk);
       if (slab_full && &c->slabs[c->cur] == s && s->epoch == my_epoch) {
         int rc2 = flush_locked(c);
         if (rc2) return rc2;
