@@ -32,6 +32,9 @@ namespace {
 
 constexpr int kTileRec = 512;                      // native records per ring stage
 constexpr int kTileBytes = kTileRec * kRecBytes;   // 20480, multiple of lcm(16,40)=80
+// Projected records: half-size stages. K-A<packed> is bound by per-CTA work (issue slots, frame barriers), not by
+// bytes in flight, so what pays is more resident CTAs per SM; smaller stages are what lets them fit.
+constexpr int kTileBytesPacked = 10240;
 // consumer warps per CTA: 8 when two CTAs share an SM, 16 when only one fits (4K grids: the sweep in
 // tools/ka_sweep.py shows one CTA of 8 consumer warps cannot keep up with HBM)
 constexpr uint32_t kEndFrame = 0xFFFFFFFFu;
@@ -69,8 +72,8 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
 // per-CTA slice of a zero-initialised global scratch (L2-resident); everything else is identical.
 // kCnt16: counters are 16-bit halves of shared-memory words (half the footprint ⇒ a deeper ring for 4K
 // grids). A vote is still one 32-bit atomicAdd on the containing word; a guard stops adding once a
-// half reaches 0x7FFF, and since at most kCons lanes × 32 merged votes can pass the guard concurrently
-// a half never carries into its neighbour. Counts >= 0x7FFF are reported as "many": exact for the
+// half reaches 0x7FFF, and since at most kCons lanes × 64 merged votes (two records per lane in the packed layout)
+// can pass the guard concurrently a half never carries into its neighbour (16 warps x 64 per trip). Counts >= 0x7FFF are reported as "many": exact for the
 // active test because VECTORS_NEEDED <= 255.
 // kPacked: the slab holds 8-byte projections of the records (bytes 6..13 of AVMotionVector: src_x, src_y,
 // dst_x, dst_y — mscan_mv8) instead of the native 40-byte layout. Same ring, same stage size; a stage then
@@ -80,15 +83,21 @@ template <bool kGlobalCnt, int kConsWarps, bool kCnt16, bool kPacked>
 __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
   static_assert(!(kGlobalCnt && kCnt16), "global counters are always 32-bit");
   constexpr uint32_t kStride = kPacked ? kPackedBytes : kRecBytes;
+  constexpr uint32_t kTile = kPacked ? kTileBytesPacked : kTileBytes;  // bytes per ring stage
   constexpr int kCons = kConsWarps * 32;
   constexpr int kThreads = kCons + 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t stages = a.stages;
   unsigned char* ring = smem;
-  TileDesc* desc = reinterpret_cast<TileDesc*>(ring + (size_t)stages * kTileBytes);
+  TileDesc* desc = reinterpret_cast<TileDesc*>(ring + (size_t)stages * kTile);
   uint64_t* bars = reinterpret_cast<uint64_t*>(desc + stages);  // full[stages], empty[stages]
   uint32_t* bits = reinterpret_cast<uint32_t*>(bars + 2 * stages);
-  uint32_t* cnt = kGlobalCnt ? a.cnt_scratch + (size_t)blockIdx.x * a.max_cells : bits + 2 * a.max_bit_words;
+  // vote marks: one byte per 32-cell word of the FLAT grid (cells [32k, 32k+32)) = "received a vote this frame".
+  // ceil(max_cells / 32) <= max_bit_words (a row-aligned word never holds more than 32 cells), so the marks fit
+  // max_bit_words bytes; the region is padded to a multiple of 16.
+  unsigned char* wordv = reinterpret_cast<unsigned char*>(bits + 2 * a.max_bit_words);
+  uint32_t* cnt = kGlobalCnt ? a.cnt_scratch + (size_t)blockIdx.x * a.max_cells
+                             : reinterpret_cast<uint32_t*>(wordv + ((a.max_bit_words + 15u) & ~15u));
 
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
@@ -104,6 +113,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
   }
   if (!kGlobalCnt)  // the global scratch is zero on entry and every epilogue leaves it zero
     for (uint32_t i = tid; i < (kCnt16 ? (a.max_cells + 1) / 2 : a.max_cells); i += kThreads) cnt[i] = 0;
+  for (uint32_t i = tid; i < a.max_bit_words; i += kThreads) wordv[i] = 0;
   __syncthreads();
 
   if (warp == 0) {
@@ -131,16 +141,16 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           const unsigned char* src = a.recs + (byte0 - d);
           // native: tile t holds records [512t, 512t+512); packed: tile t holds the records that lie in
           // bytes [20480t, 20480t+20480) of the 16-byte aligned stream starting at src
-          const uint32_t n_tiles = kPacked ? (uint32_t)((d + (uint64_t)kPackedBytes * n + kTileBytes - 1) / kTileBytes)
+          const uint32_t n_tiles = kPacked ? (uint32_t)((d + (uint64_t)kPackedBytes * n + kTile - 1) / kTile)
                                            : (n + kTileRec - 1) / kTileRec;
           for (uint32_t t = 0; t < n_tiles; ++t) {
             uint32_t nr, bytes, boff;
             if (kPacked) {
-              const uint32_t r_lo = t ? (uint32_t)(((uint64_t)t * kTileBytes - d) / kPackedBytes) : 0u;
-              const uint32_t r_hi = (uint32_t)min((uint64_t)n, ((uint64_t)(t + 1) * kTileBytes - d) / kPackedBytes);
+              const uint32_t r_lo = t ? (uint32_t)(((uint64_t)t * kTile - d) / kPackedBytes) : 0u;
+              const uint32_t r_hi = (uint32_t)min((uint64_t)n, ((uint64_t)(t + 1) * kTile - d) / kPackedBytes);
               nr = r_hi - r_lo;
               boff = t ? 0u : d;
-              bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((boff + kPackedBytes * nr + 15u) & ~15u);
+              bytes = (t + 1 < n_tiles) ? kTile : ((boff + kPackedBytes * nr + 15u) & ~15u);
             } else {
               nr = min((uint32_t)kTileRec, n - t * kTileRec);
               boff = d;
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
               // 16 useful bytes, rounded up to 16 (never past the record's own 40 bytes)
               bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((d + kRecBytes * (nr - 1) + 16u + 15u) & ~15u);
             }
-            mbar_wait(bar_empty0 + 8 * stage, phase ^ 1u);
+            mbar_wait<kPacked>(bar_empty0 + 8 * stage, phase ^ 1u);
             TileDesc td;
             td.n_rec = nr;
             td.byte_off = boff;
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
             td.y_max = m_cur.g.y_max;
             desc[stage] = td;
             mbar_arrive_expect_tx(bar_full0 + 8 * stage, bytes);
-            bulk_g2s(smem_u32(ring + (size_t)stage * kTileBytes), src + (size_t)t * kTileBytes, bytes,
+            bulk_g2s(smem_u32(ring + (size_t)stage * kTile), src + (size_t)t * kTile, bytes,
                      bar_full0 + 8 * stage, policy);
             if (++stage == stages) {
               stage = 0;
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
         f_next = f_next2;
       }
       // terminal descriptor
-      mbar_wait(bar_empty0 + 8 * stage, phase ^ 1u);
+      mbar_wait<kPacked>(bar_empty0 + 8 * stage, phase ^ 1u);
       desc[stage].frame = kEndFrame;
       desc[stage].n_rec = 0;
       mbar_arrive(bar_full0 + 8 * stage);
@@ -189,55 +199,114 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
     uint32_t stage = 0, phase = 0, fseq = 0;
     bool voted = false;
     while (true) {
-      mbar_wait(bar_full0 + 8 * stage, phase);
+      mbar_wait<kPacked>(bar_full0 + 8 * stage, phase);
       const TileDesc td = desc[stage];
       if (td.frame == kEndFrame) break;
-      const unsigned char* base = ring + (size_t)stage * kTileBytes + td.byte_off;
       const int32_t gw = td.gw;
       const uint32_t live_rows = (uint32_t)(td.y_max - td.y_min);
-      for (uint32_t r0 = cwarp * 32; r0 < td.n_rec; r0 += kCons) {
-        const uint32_t r = r0 + lane;
-        int32_t key = -1;
-        if (r < td.n_rec) {
-          int32_t sx, sy, tx, ty;
-          if (kPacked) {
-            const uint2 w = *reinterpret_cast<const uint2*>(base + (size_t)r * kPackedBytes);  // src_x | src_y<<16, dst_x | dst_y<<16
-            sx = (int32_t)(int16_t)(w.x & 0xFFFFu);
-            sy = (int32_t)w.x >> 16;
-            tx = (int32_t)(int16_t)(w.y & 0xFFFFu);
-            ty = (int32_t)w.y >> 16;
-          } else {
+      // one vote of `amount` for cell `key` (:265-266), with the carry guard of the 16-bit layout; the 32-cell word of
+      // the flat grid that holds the cell is marked so that the epilogue only visits words that received votes
+      auto vote = [&](int32_t key, int32_t, uint32_t amount) {
+        if (kCnt16) {
+          uint32_t* w = &cnt[(uint32_t)key >> 1];
+          const uint32_t sh = ((uint32_t)key & 1u) * 16u;
+          if (((*reinterpret_cast<volatile uint32_t*>(w) >> sh) & 0xFFFFu) < 0x7FFFu) atomicAdd(w, amount << sh);
+        } else {
+          atomicAdd(&cnt[key], amount);
+        }
+        wordv[key >> 5] = 1;  // (the key's 32-cell word of the flat grid: what the epilogue has to look at)
+      };
+      // exact int32 test of :246-262 on one record; returns the cell key or -1, and the cell's row
+      auto key_of = [&](int32_t sx, int32_t sy, int32_t tx, int32_t ty, int32_t* gy_out) -> int32_t {
+        const int32_t dx = tx - sx, dy = ty - sy;                                                    // :246-247
+        const int32_t mag = (int32_t)((uint32_t)dx * (uint32_t)dx + (uint32_t)dy * (uint32_t)dy);    // :248
+        const int32_t gx = tx >> shift, gy = ty >> shift;                                            // :255-256
+        const bool in = ((uint32_t)gx < (uint32_t)gw) && ((uint32_t)(gy - td.y_min) < live_rows);    // :262
+        *gy_out = gy;
+        return (mag >= ithr && in) ? gy * gw + gx : -1;                                              // :251
+      };
+      if (kPacked) {
+        // Projected records, two per lane: one LDS.128 per 16-byte slot of the stage. A record whose src equals its dst
+        // (w.x == w.y: a static macroblock — about 90 % of a CCTV stream) has mag_sq == 0 and cannot vote while the
+        // threshold is positive, so one compare per record decides, and a warp trip without a moving record costs the
+        // loads, the compares and one vote.any. Survivors go through the exact test above. Slots past the tile's end
+        // are loaded too (the address stays inside this CTA's shared memory) and masked by the record-index test.
+        const uint4* sp = reinterpret_cast<const uint4*>(ring + (size_t)stage * kTile);
+        const uint32_t o = td.byte_off >> 3;  // 0 or 1: the stage's first 8 bytes precede the tile's first record
+        const uint32_t n_rec = td.n_rec;
+        const uint32_t n_slots = (td.byte_off + (uint32_t)kPackedBytes * n_rec + 15u) >> 4;
+        const bool skip_static = ithr > 0;
+        // records 2j - o (first half of slot j) and 2j + 1 - o (second half); unsigned compares reject the halves that
+        // are not records of this tile
+        auto slot = [&](uint32_t j, const uint4& w) {
+          const uint32_t ra = 2u * j - o;
+          const bool ma = (ra < n_rec) && (!skip_static || w.x != w.y);
+          const bool mb = (ra + 1u < n_rec) && (!skip_static || w.z != w.w);
+          if (!__any_sync(0xffffffffu, ma || mb)) return;
+          int32_t gya = 0, gyb = 0;
+          const int32_t ka = ma ? key_of((int32_t)(int16_t)(w.x & 0xFFFFu), (int32_t)w.x >> 16, (int32_t)(int16_t)(w.y & 0xFFFFu), (int32_t)w.y >> 16, &gya) : -1;
+          const int32_t kb = mb ? key_of((int32_t)(int16_t)(w.z & 0xFFFFu), (int32_t)w.z >> 16, (int32_t)(int16_t)(w.w & 0xFFFFu), (int32_t)w.w >> 16, &gyb) : -1;
+          if (!__any_sync(0xffffffffu, (ka & kb) >= 0)) return;  // (ka & kb) >= 0  ⇔  ka >= 0 || kb >= 0
+          // lane-level run-length merge: a lane whose two records vote for one cell (or only one of them votes) is one
+          // item; lanes with two different cells vote twice on their own
+          const bool mixed = ka >= 0 && kb >= 0 && ka != kb;
+          const int32_t K = mixed ? (-2 - (int32_t)lane) : (ka >= 0 ? ka : kb);
+          const uint32_t two = __ballot_sync(0xffffffffu, !mixed && ka >= 0 && kb >= 0);
+          const int32_t prev = __shfl_up_sync(0xffffffffu, K, 1);
+          const bool head = (lane == 0) || (K != prev);
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          if (mixed) {
+            vote(ka, gya, 1u);
+            vote(kb, gyb, 1u);
+            voted = true;
+          } else if (head && K >= 0) {
+            const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
+            const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
+            const uint32_t run = (next == 32u ? 0xFFFFFFFFu : ((1u << next) - 1u)) & (0xFFFFFFFFu << lane);  // lanes [lane, next)
+            vote(K, ka >= 0 ? gya : gyb, (next - lane) + (uint32_t)__popc(two & run));
+            voted = true;
+          }
+        };
+        if (keep_any) {
+          uint32_t j = cwarp * 32 + lane;
+          for (; j - lane + kCons < n_slots; j += 2 * kCons) {  // two slots per lane per trip: both loads in flight together
+            const uint4 w0 = sp[j], w1 = sp[j + kCons];
+            if (skip_static) {
+              const uint32_t ra0 = 2u * j - o, ra1 = ra0 + 2u * kCons;
+              const bool m = ((ra0 < n_rec) && w0.x != w0.y) || ((ra0 + 1u < n_rec) && w0.z != w0.w) ||
+                             ((ra1 < n_rec) && w1.x != w1.y) || ((ra1 + 1u < n_rec) && w1.z != w1.w);
+              if (!__any_sync(0xffffffffu, m)) continue;
+            }
+            slot(j, w0);
+            slot(j + kCons, w1);
+          }
+          if (j - lane < n_slots) slot(j, sp[j]);
+        }
+      } else {
+        const unsigned char* base = ring + (size_t)stage * kTile + td.byte_off;
+        for (uint32_t r0 = cwarp * 32; r0 < td.n_rec; r0 += kCons) {
+          const uint32_t r = r0 + lane;
+          int32_t key = -1, gy = 0;
+          if (r < td.n_rec) {
             const unsigned char* p = base + (size_t)r * kRecBytes;
             const uint32_t w1 = *reinterpret_cast<const uint32_t*>(p + 4);  // w | h<<8 | src_x<<16
             const uint2 w23 = *reinterpret_cast<const uint2*>(p + 8);       // src_y | dst_x<<16, dst_y | pad<<16
-            sx = (int32_t)w1 >> 16;
-            sy = (int32_t)(int16_t)(w23.x & 0xFFFFu);
-            tx = (int32_t)w23.x >> 16;
-            ty = (int32_t)(int16_t)(w23.y & 0xFFFFu);
+            const int32_t k = key_of((int32_t)w1 >> 16, (int32_t)(int16_t)(w23.x & 0xFFFFu), (int32_t)w23.x >> 16,
+                                     (int32_t)(int16_t)(w23.y & 0xFFFFu), &gy);
+            if (keep_any) key = k;
           }
-          const int32_t dx = tx - sx, dy = ty - sy;                        // :246-247
-          const int32_t mag = (int32_t)((uint32_t)dx * (uint32_t)dx + (uint32_t)dy * (uint32_t)dy);  // :248
-          const int32_t gx = tx >> shift, gy = ty >> shift;                // :255-256
-          const bool in = ((uint32_t)gx < (uint32_t)gw) && ((uint32_t)(gy - td.y_min) < live_rows);  // :262
-          if (keep_any && mag >= ithr && in) key = gy * gw + gx;           // :251
-        }
-        // nothing to vote in this warp trip (static macroblocks: the common CCTV case) — skip the merge
-        if (!__any_sync(0xffffffffu, key >= 0)) continue;
-        // run-length merge of equal neighbouring keys inside the warp
-        const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (lane == 0) || (key != prev);
-        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        if (head && key >= 0) {
-          const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
-          const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
-          if (kCnt16) {
-            uint32_t* w = &cnt[(uint32_t)key >> 1];
-            const uint32_t sh = ((uint32_t)key & 1u) * 16u;
-            if (((*reinterpret_cast<volatile uint32_t*>(w) >> sh) & 0xFFFFu) < 0x7FFFu) atomicAdd(w, (next - lane) << sh);
-          } else {
-            atomicAdd(&cnt[key], next - lane);                             // :265-266
+          // nothing to vote in this warp trip (static macroblocks: the common CCTV case) — skip the merge
+          if (!__any_sync(0xffffffffu, key >= 0)) continue;
+          // run-length merge of equal neighbouring keys inside the warp
+          const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+          const bool head = (lane == 0) || (key != prev);
+          const uint32_t heads = __ballot_sync(0xffffffffu, head);
+          if (head && key >= 0) {
+            const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
+            const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
+            vote(key, gy, next - lane);
+            voted = true;
           }
-          voted = true;
         }
       }
       __syncwarp();
@@ -250,30 +319,47 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
         // ---- frame epilogue: Phase 2 (:272-294) -------------------------------------------------
         const bool any = named_bar_or(kBarCons, kCons, voted);
         voted = false;
-        if (any || vec_need == 0) {
+        const uint32_t wpr = (uint32_t)(gw + 31) >> 5;
+        if ((any || vec_need == 0) && wpr != 0) {
           const int32_t gh = td.gh;
-          const uint32_t wpr = (uint32_t)(gw + 31) >> 5;
+          const bool all_words = vec_need == 0;  // every cell is active, voted or not
           uint32_t* brow = bits + (fseq & 1u) * a.max_bit_words;
-          // pass 1: counters → active bit-rows, counters re-zeroed for the next frame
-          for (int32_t y = (int32_t)cwarp; y < gh; y += kConsWarps) {
-            for (uint32_t w = 0; w < wpr; ++w) {
-              const int32_t x = (int32_t)(w * 32 + lane);
+          // pass 1: counters → active bit-rows (:282), counters re-zeroed for the next frame (:229). Votes marked the
+          // 32-cell words of the FLAT grid (cells [32k, 32k+32)) they fell into; only those are read. A flat word k
+          // spans at most two grid rows; its cells are turned into bits of the row-aligned bit-row words with atomicOr
+          // after the bit-rows have been cleared.
+          const uint32_t n_bw = (uint32_t)gh * wpr;
+          for (uint32_t i = ctid; i < n_bw; i += kCons) brow[i] = 0;
+          named_bar_sync(kBarCons, kCons);
+          const uint32_t n_cells = (uint32_t)gh * (uint32_t)gw;
+          const uint32_t n_fw = (n_cells + 31u) >> 5;
+          for (uint32_t k0 = cwarp * 32; k0 < n_fw; k0 += kCons) {
+            const uint32_t k = k0 + lane;
+            const bool mine = k < n_fw && (all_words || wordv[k]);
+            if (mine) wordv[k] = 0;
+            uint32_t todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {  // the whole warp reads one marked word: 32 cells
+              const uint32_t kk = k0 + (uint32_t)(__ffs(todo) - 1);
+              todo &= todo - 1;
+              const uint32_t cell = kk * 32 + lane;
               uint32_t c = 0;
-              const bool valid = x < gw;
+              const bool valid = cell < n_cells;
               if (valid) {
                 if (kCnt16) {
-                  uint16_t* h = reinterpret_cast<uint16_t*>(cnt) + (y * gw + x);
+                  uint16_t* h = reinterpret_cast<uint16_t*>(cnt) + cell;
                   c = *h;
                   *h = 0;
                 } else {
                   // global counters are voted with L2 atomics: read them past L1 (a plain load could
                   // return this SM's stale line from the previous frame)
-                  c = kGlobalCnt ? __ldcg(&cnt[y * gw + x]) : cnt[y * gw + x];
-                  cnt[y * gw + x] = 0;
+                  c = kGlobalCnt ? __ldcg(&cnt[cell]) : cnt[cell];
+                  cnt[cell] = 0;
                 }
               }
-              const uint32_t word = __ballot_sync(0xffffffffu, valid && c >= vec_need);  // :282
-              if (lane == 0) brow[(uint32_t)y * wpr + w] = word;
+              if (valid && c >= vec_need) {  // :282
+                const uint32_t y = cell / (uint32_t)gw, x = cell - y * (uint32_t)gw;
+                atomicOr(&brow[y * wpr + (x >> 5)], 1u << (x & 31u));
+              }
             }
           }
           named_bar_sync(kBarCons, kCons);
@@ -335,9 +421,9 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
 
 constexpr uint32_t kSmemReserve = 1024;  // per-CTA driver reservation
 
-uint32_t smem_for(uint32_t stages, uint32_t counter_bytes, uint32_t max_bit_words) {
-  return stages * (uint32_t)kTileBytes + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
-         2 * max_bit_words * 4u + ((counter_bytes + 15u) & ~15u) + 128u;
+uint32_t smem_for(uint32_t stages, uint32_t counter_bytes, uint32_t max_bit_words, bool packed) {
+  return stages * (uint32_t)(packed ? kTileBytesPacked : kTileBytes) + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
+         2 * max_bit_words * 4u + ((max_bit_words + 15u) & ~15u) + ((counter_bytes + 15u) & ~15u) + 128u;  // 2 bit-row buffers + vote marks
 }
 
 // Tuning overrides for experiments (tools/ka_sweep.py): MSCAN_KA_CTAS, MSCAN_KA_STAGES, MSCAN_KA_WARPS, MSCAN_KA_CNT16.
@@ -347,10 +433,10 @@ uint32_t env_u32(const char* name) {
 }
 
 // largest ring depth in [lo, hi] that fits `ctas` CTAs per SM; 0 if none
-uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, uint32_t smem_optin, uint32_t lo, uint32_t hi) {
+uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, uint32_t smem_optin, uint32_t lo, uint32_t hi, bool packed) {
   const uint32_t sm_total = 228u * 1024u;
   for (uint32_t st = hi; st >= lo; --st) {
-    const uint32_t need = smem_for(st, counter_bytes, bit_words);
+    const uint32_t need = smem_for(st, counter_bytes, bit_words, packed);
     if (need <= smem_optin && ctas * (need + kSmemReserve) <= sm_total) return st;
   }
   return 0;
@@ -366,13 +452,13 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
     plan->cnt16 = cnt16;
     plan->global_cnt = global_cnt;
     plan->cons_warps = ctas == 1 ? 16 : 8;
-    plan->smem_bytes = smem_for(st, global_cnt ? 0u : (cnt16 ? b16 : b32), max_bit_words);
+    plan->smem_bytes = smem_for(st, global_cnt ? 0u : (cnt16 ? b16 : b32), max_bit_words, packed);
     return true;
   };
   const uint32_t want_st = env_u32("MSCAN_KA_STAGES"), want_ctas = env_u32("MSCAN_KA_CTAS");
-  if (want_st >= 2 && want_st <= 10 && want_ctas >= 1 && want_ctas <= 4) {
+  if (want_st >= 2 && want_st <= 16 && want_ctas >= 1 && want_ctas <= 6) {
     const uint32_t c16 = env_u32("MSCAN_KA_CNT16") ? 1u : 0u;
-    if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st)) {
+    if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st, packed)) {
       set(want_ctas, want_st, c16, 0);
       const uint32_t w = env_u32("MSCAN_KA_WARPS");
       if (w == 8 || w == 16) plan->cons_warps = w;
@@ -381,11 +467,13 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
   }
   uint32_t st;
   if (packed) {
-    // Projected records carry 5x fewer bytes per vote: K-A<packed> is bound by instruction issue, not by
-    // HBM, so the plan buys resident warps with ring depth (sweep: profiles/r02_ka_sweep_packed.log —
-    // 1080p 3 CTAs x 8 warps x 2 stages 420 G rec/s vs 326 for the native plan; 4K 2 x 16 x 2 431 vs 346)
-    if ((st = fit_stages(3, b16, max_bit_words, smem_optin, 2, 2))) return set(3, st, 1, 0);
-    if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 2, 2))) {
+    // Projected records carry 5x fewer bytes per vote: K-A<packed> is bound by per-CTA work (issue slots, the frame
+    // barriers), not by HBM, so the plan buys resident CTAs with ring depth — half-size stages (10 KB) are what lets a
+    // fourth CTA fit at 1080p (sweep profiles/r03_ka_sweep_packed.log: 4 CTAs x 8 warps x 3 stages 556 G rec/s,
+    // 5 x 8 x 2 517, 3 x 8 x 4 482; 16-warp CTAs are slower)
+    if ((st = fit_stages(4, b16, max_bit_words, smem_optin, 3, 3, packed))) return set(4, st, 1, 0);
+    if ((st = fit_stages(3, b16, max_bit_words, smem_optin, 2, 4, packed))) return set(3, st, 1, 0);
+    if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 2, 4, packed))) {
       set(2, st, 1, 0);
       plan->cons_warps = 16;
       return true;
@@ -393,16 +481,16 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
   }
   // 1-4: two CTAs per SM; a 4-stage ring (160 KB in flight per SM) measures ~1.3 % faster than 3 stages
   // (tools/ka_sweep.py), so 16-bit counters are preferred when they are what makes the 4th stage fit
-  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4))) return set(2, st, 0, 0);
-  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 4, 4))) return set(2, st, 1, 0);
-  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 3, 3))) return set(2, st, 0, 0);
-  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 3, 3))) return set(2, st, 1, 0);
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4, packed))) return set(2, st, 0, 0);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 4, 4, packed))) return set(2, st, 1, 0);
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 3, 3, packed))) return set(2, st, 0, 0);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 3, 3, packed))) return set(2, st, 1, 0);
   // 5-7: one CTA per SM with 16 consumer warps and as deep a ring as fits (4K: u16 counters give 7 stages)
-  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 6, 8))) return set(1, st, 0, 0);
-  if ((st = fit_stages(1, b16, max_bit_words, smem_optin, 2, 8))) return set(1, st, 1, 0);
-  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 2, 8))) return set(1, st, 0, 0);
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 6, 8, packed))) return set(1, st, 0, 0);
+  if ((st = fit_stages(1, b16, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 1, 0);
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 0, 0);
   // 8: counters in global memory (8K and larger)
-  if ((st = fit_stages(1, 0, max_bit_words, smem_optin, 2, 8))) return set(1, st, 0, 1);
+  if ((st = fit_stages(1, 0, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 0, 1);
   return false;
 }
 

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) ka_scan_cluster_kernel(const __gr
               boff = d;
               bytes = (t + 1 < n_tiles) ? (uint32_t)kTileBytes : ((d + kRecBytes * (nr - 1) + 16u + 15u) & ~15u);
             }
-            mbar_wait(bar_empty0 + 8 * stage, phase ^ 1u);
+            mbar_wait<kPacked>(bar_empty0 + 8 * stage, phase ^ 1u);
             desc[stage] = SliceTile{nr, boff, 0u, 0u};
             mbar_arrive_expect_tx(bar_full0 + 8 * stage, bytes);
             bulk_g2s(smem_u32(ring + (size_t)stage * kTileBytes), src + (size_t)t * kTileBytes, bytes, bar_full0 + 8 * stage, policy);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) ka_scan_cluster_kernel(const __gr
             }
           }
         }
-        mbar_wait(bar_empty0 + 8 * stage, phase ^ 1u);  // end-of-slice marker
+        mbar_wait<kPacked>(bar_empty0 + 8 * stage, phase ^ 1u);  // end-of-slice marker
         desc[stage] = SliceTile{0u, 0u, 0u, 0u};
         mbar_arrive(bar_full0 + 8 * stage);
         if (++stage == stages) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) ka_scan_cluster_kernel(const __gr
       const uint32_t live_rows = (uint32_t)(y_max - y_min);
       const uint32_t cnt_addr = smem_u32(cnt);
       while (true) {
-        mbar_wait(bar_full0 + 8 * stage, phase);
+        mbar_wait<kPacked>(bar_full0 + 8 * stage, phase);
         const SliceTile td = desc[stage];
         if (td.n_rec) {
           const unsigned char* base = ring + (size_t)stage * kTileBytes + td.byte_off;

@@ -54,7 +54,8 @@ def main():
     wl = sys.argv[2] if len(sys.argv) > 2 else "stream"
     layout = sys.argv[3] if len(sys.argv) > 3 else "native"  # or "packed" (mscan_mv8 records)
     preset, seed, fixed = WORKLOADS[wl]
-    plans = [(0, 0, 0, 0), (2, 2, 8, 1), (3, 2, 8, 1), (2, 2, 16, 1), (2, 3, 16, 1), (2, 4, 16, 1), (3, 2, 16, 1), (1, 4, 16, 1)] if layout == "packed" else [(0, 0, 0, 0), (1, 4, 16, 0), (1, 4, 16, 1), (1, 6, 16, 1), (1, 7, 16, 1), (1, 8, 16, 0), (1, 8, 16, 1), (1, 9, 16, 0),
+    plans = [(0, 0, 0, 0), (3, 2, 8, 1), (3, 3, 8, 1), (3, 4, 8, 1), (4, 2, 8, 1), (4, 3, 8, 1), (4, 4, 8, 1), (5, 2, 8, 1), (5, 3, 8, 1), (6, 2, 8, 1),
+             (2, 4, 16, 1), (3, 2, 16, 1), (3, 4, 16, 1), (2, 8, 8, 1)] if layout == "packed" else [(0, 0, 0, 0), (1, 4, 16, 0), (1, 4, 16, 1), (1, 6, 16, 1), (1, 7, 16, 1), (1, 8, 16, 0), (1, 8, 16, 1), (1, 9, 16, 0),
              (1, 9, 16, 1), (1, 10, 16, 1), (2, 3, 8, 0), (2, 4, 8, 0), (2, 4, 8, 1), (2, 5, 8, 1), (3, 2, 8, 0), (3, 3, 8, 1)]
     for ctas, st, warps, c16 in plans:
         env = dict(os.environ)
