@@ -14,6 +14,7 @@
  *   mscan_video_open        <- grid/margin derivation src/motion_scanner.cpp:189-199
  *   mscan_submit            <- the per-frame call `check_frame(frame)` src/motion_scanner.cpp:376
  *                              (decl include/motion_trim/motion_scanner.hpp:106), batched
+ *   mscan_submit_device     <- same call site, records already in device memory (no host staging)
  *   mscan_submit_packed / mscan_pack_records / mscan_mv8
  *                           <- same call site; the record is the byte range [6,14) of AVMotionVector,
  *                              i.e. exactly the fields read at src/motion_scanner.cpp:243-256
@@ -153,6 +154,9 @@ typedef struct mscan_ctx mscan_ctx;
 /* ---- library-level ----------------------------------------------------- */
 int mscan_abi_version(void);
 int mscan_device_count(int* n_out);            /* MSCAN_ERR_CUDA when no driver/GPU */
+/* "0000:3b:00.0"-style id of a device (len >= 13): lets a host look up the CPUs local to the GPU
+ * (/sys/bus/pci/devices/<id>/local_cpulist) when it pins its decode threads */
+int mscan_device_pci_bus_id(int device, char* buf, int len);
 const char* mscan_status_string(int status);
 
 /* config.hpp:56-125 code defaults */
@@ -183,7 +187,9 @@ int mscan_video_open(mscan_ctx* ctx, uint32_t video_id, int width, int height);
 int mscan_video_open_geometry(mscan_ctx* ctx, uint32_t video_id, const mscan_geometry* g);
 /* Append n_frames frames of one video. recs holds the frames' records back to back in FFmpeg's
  * native layout; rec_count[i] == 0 means "no MV side data" (motion_scanner.cpp:219-221).
- * Asynchronous. If recs lies in pinned memory (mscan_host_alloc / mscan_host_register /
+ * Asynchronous, and callable concurrently from many decode threads (one scanner per thread in the reference,
+ * include/motion_trim/motion_scanner.hpp:8-13): a call reserves its place under the context's mutex for a few
+ * hundred ns and moves its records outside it, so the threads project their own cache-hot side data in parallel. If recs lies in pinned memory (mscan_host_alloc / mscan_host_register /
  * cudaHostRegister) it is DMA'd in place and must stay valid until the copy has completed, i.e. until
  * mscan_host_fence, mscan_sync, mscan_collect* or mscan_segments* returns (mscan_flush only enqueues);
  * pageable memory is consumed before the call returns: its records are projected to mscan_mv8 (the 8
@@ -198,6 +204,17 @@ int mscan_submit(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const dou
  * may be mixed freely, also within one video: a slab (= one K-A launch) holds one format. */
 int mscan_submit_packed(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
                         const uint32_t* rec_count, const mscan_mv8* recs, uint64_t* first_frame_out);
+/* Same call site, for producers whose records already lie in THIS GPU's memory (another GPU stage, a GPUDirect-storage
+ * read of an MV stream file): the frames join the video's frame log like a host submit — so mscan_collect* /
+ * mscan_segments* / mscan_video_append_from work on them unchanged — and K-A scans the caller's buffer in place on the
+ * context's own stream; only 16 bytes of metadata per frame cross PCIe. d_recs: 16-byte aligned device pointer to the
+ * frames' records back to back, native (packed == 0) or mscan_mv8 (packed != 0; readable for 16 bytes past the last
+ * record). pts / rec_count: host arrays. ready_stream: CUDA stream on which the records become ready (the scan is
+ * ordered after the work already enqueued on it), NULL if they are ready now. The buffer must stay valid until a
+ * mscan_collect* / mscan_segments* / mscan_video_close / mscan_sync that covers these frames has returned. */
+int mscan_submit_device(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
+                        const uint32_t* rec_count, const void* d_recs, int packed, void* ready_stream,
+                        uint64_t* first_frame_out);
 /* The projection itself, usable from any thread without a context or a GPU: out[i] = bytes 6..13 of
  * recs[i]. out must be 8-byte aligned; written with streaming stores (it is read next by the DMA engine). */
 int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out);

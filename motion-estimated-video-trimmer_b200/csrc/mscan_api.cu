@@ -72,6 +72,7 @@ struct Video {
   // epoch of each slab when this video last put frames into it: equal to the slab's current epoch ⇔ results
   // of this video may still be pending there (what collect / segments / close have to wait for — nothing else)
   uint64_t slab_epoch[kSlabs] = {0, 0, 0};
+  uint64_t dev_seq = 0;  // mscan_submit_device: sequence number of this video's last launch on the context's dev_stream
 };
 
 struct Slab {
@@ -115,6 +116,20 @@ struct EvPair {
 
 constexpr uint64_t kPoolChunk = 32768;      // records per work item (1.3 MB of native records)
 constexpr uint64_t kPoolMinRecs = 1 << 18;  // smaller jobs are projected by the calling thread alone
+
+// The CPUs the PROCESS may run on, captured the first time the library is used (mscan_create, normally from the main
+// thread): decode threads are often pinned to a few CPUs each (src/system.cpp:211-225), and the shared projection pool
+// must not inherit the mask of whichever of them happens to start it.
+const cpu_set_t& process_cpus() {
+  static const cpu_set_t mask = [] {
+    cpu_set_t m;
+    CPU_ZERO(&m);
+    if (sched_getaffinity(0, sizeof m, &m) != 0 || CPU_COUNT(&m) == 0)
+      for (int i = 0; i < (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), CPU_SETSIZE); ++i) CPU_SET(i, &m);
+    return m;
+  }();
+  return mask;
+}
 
 // Parallel-for over one projection job; the calling thread takes part. ONE pool per process, shared by every
 // context (a pool per GPU context sized for the whole box would oversubscribe it n-fold, one sized cores/n would
@@ -169,6 +184,7 @@ class PackPool {
     }
   }
   void worker(int index) {
+    sched_setaffinity(0, sizeof(cpu_set_t), &process_cpus());  // not the (possibly pinned) creator's mask
     uint64_t seen = 0;
     for (;;) {
       const uint8_t* src;
@@ -208,10 +224,7 @@ class PackPool {
 
 int default_pack_threads() {
   if (const char* e = std::getenv("MSCAN_PACK_THREADS")) return std::max(1, std::atoi(e));
-  cpu_set_t set;
-  int n = 0;
-  if (sched_getaffinity(0, sizeof set, &set) == 0) n = CPU_COUNT(&set);  // honours taskset / cgroup cpusets
-  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  const int n = CPU_COUNT(&process_cpus());  // honours taskset / cgroup cpusets
   return std::max(1, std::min(n, 64));
 }
 
@@ -323,6 +336,13 @@ struct mscan_ctx {
 
   uint32_t* d_work = nullptr;  // kWorkSlots × {next, done}
   uint32_t work_rr = 0;
+  // a rotating slot is reused only after the launch that last used it: the next user's stream waits for this event
+  cudaEvent_t slot_ev[kWorkSlots] = {};
+  bool slot_used[kWorkSlots] = {};
+  // mscan_submit_device: launches on records that already lie in device memory
+  cudaStream_t dev_stream = nullptr;
+  cudaEvent_t dev_done = nullptr, dev_ready = nullptr;
+  uint64_t dev_seq = 0, dev_done_seq = 0;  // launches issued on dev_stream / known complete
   uint32_t* d_cnt_scratch = nullptr;  // global vote counters for grids beyond shared memory (zeroed)
   uint64_t cnt_scratch_elems = 0;
   uint32_t adj8 = 0;
@@ -498,7 +518,15 @@ int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaSt
   ScanArgs a = args_in;
   // two kernels must never share a frame queue while both run: a slab's launches are ordered by its stream, so
   // the slab index is a safe slot; launches on caller streams rotate through the remaining slots
-  const uint32_t slot = slab_index >= 0 ? (uint32_t)slab_index : (uint32_t)kSlabs + (c->work_rr++ % (uint32_t)(kWorkSlots - kSlabs));
+  // slab_index >= 0: that slab's stream; kSlabs: the context's dev_stream; -1: a caller stream → rotating slots, each
+  // guarded by the event of its previous user (two kernels sharing a queue while both run would split the frames)
+  uint32_t slot;
+  if (slab_index >= 0) {
+    slot = (uint32_t)slab_index;
+  } else {
+    slot = (uint32_t)kSlabs + 1u + (c->work_rr++ % (uint32_t)(kWorkSlots - kSlabs - 1));
+    if (c->slot_used[slot]) CU(cudaStreamWaitEvent(st, c->slot_ev[slot], 0));
+  }
   a.work = c->d_work + 2 * slot;
   a.adj8 = c->adj8;
   a.cnt_scratch = nullptr;
@@ -549,6 +577,10 @@ int run_scan(mscan_ctx* c, const ScanArgs& args_in, const ScanPlan& plan, cudaSt
   if (c->profiling) {
     cudaEventRecord(ev.b, st);
     c->ev_pending.push_back(ev);
+  }
+  if (slab_index < 0) {
+    CU(cudaEventRecord(c->slot_ev[slot], st));
+    c->slot_used[slot] = true;
   }
   c->stats.scan_launches += 1;
   c->stats.frames_scanned += a.n_frames;
@@ -705,6 +737,10 @@ int flush_locked(mscan_ctx* c) {
 int sync_scans_locked(mscan_ctx* c) {
   int rc = flush_locked(c);
   if (rc) return rc;
+  if (c->dev_seq != c->dev_done_seq) {
+    CU(cudaStreamSynchronize(c->dev_stream));
+    c->dev_done_seq = c->dev_seq;
+  }
   for (auto& s : c->slabs)
     if (s.in_flight) {
       CU(cudaEventSynchronize(s.done));
@@ -741,12 +777,21 @@ int sync_videos(mscan_ctx* c, std::unique_lock<std::mutex>& lk, const uint32_t* 
     }
     if (s.in_flight) waits[n_wait++] = Wait{k, s.epoch, s.launch_seq, s.done};
   }
-  if (n_wait == 0) return MSCAN_OK;
+  uint64_t dev_need = 0;  // frames handed over with mscan_submit_device
+  for (uint32_t i = 0; i < n_ids; ++i) {
+    auto it = c->videos.find(ids[i]);
+    if (it != c->videos.end()) dev_need = std::max(dev_need, it->second.dev_seq);
+  }
+  const bool dev_wait = dev_need > c->dev_done_seq;
+  const uint64_t dev_seq_now = c->dev_seq;  // what dev_done covers when we wait on it
+  if (n_wait == 0 && !dev_wait) return MSCAN_OK;
   lk.unlock();
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < n_wait && e == cudaSuccess; ++i) e = cudaEventSynchronize(waits[i].ev);
+  if (dev_wait && e == cudaSuccess) e = cudaEventSynchronize(c->dev_done);
   lk.lock();
   if (e != cudaSuccess) return fail(c, MSCAN_ERR_CUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+  if (dev_wait) c->dev_done_seq = std::max(c->dev_done_seq, dev_seq_now);
   for (int i = 0; i < n_wait; ++i) {
     Slab& s = c->slabs[waits[i].k];
     if (s.epoch == waits[i].epoch && s.launch_seq == waits[i].seq && s.in_flight) {  // nothing was launched on it meanwhile
@@ -981,6 +1026,7 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
     cudaGetLastError();
     return MSCAN_ERR_CUDA;  // no CPU fallback
   }
+  process_cpus();  // capture the process's CPU mask before the caller starts pinning threads
   mscan_ctx* c = new (std::nothrow) mscan_ctx();
   if (!c) return MSCAN_ERR_NOMEM;
   c->device = device;
@@ -1020,6 +1066,10 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   c->smem_optin = (uint32_t)v;
   CUB_(scan_configure(c->smem_optin));
   CUB_(cudaStreamCreateWithFlags(&c->main_stream, cudaStreamNonBlocking));
+  CUB_(cudaStreamCreateWithFlags(&c->dev_stream, cudaStreamNonBlocking));
+  CUB_(cudaEventCreateWithFlags(&c->dev_done, cudaEventDisableTiming));
+  CUB_(cudaEventCreateWithFlags(&c->dev_ready, cudaEventDisableTiming));
+  for (auto& e : c->slot_ev) CUB_(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUB_(cudaMalloc((void**)&c->d_geoms, sizeof(DevGeom) * kMaxGeoms));
   CUB_(cudaMalloc((void**)&c->d_work, sizeof(uint32_t) * 2 * kWorkSlots));
   CUB_(cudaMemset(c->d_work, 0, sizeof(uint32_t) * 2 * kWorkSlots));
@@ -1098,6 +1148,11 @@ int mscan_destroy(mscan_ctx* c) {
   if (c->h_exts) cudaFreeHost(c->h_exts);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->main_stream) cudaStreamDestroy(c->main_stream);
+  if (c->dev_stream) cudaStreamDestroy(c->dev_stream);
+  if (c->dev_done) cudaEventDestroy(c->dev_done);
+  if (c->dev_ready) cudaEventDestroy(c->dev_ready);
+  for (auto& e : c->slot_ev)
+    if (e) cudaEventDestroy(e);
   cudaGetLastError();
   delete c;
   return MSCAN_OK;
@@ -1415,6 +1470,107 @@ int mscan_submit_packed(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
                         const mscan_mv8* recs, uint64_t* first_frame_out) {
   if (recs && (reinterpret_cast<uintptr_t>(recs) & 7u)) return fail(c, MSCAN_ERR_INVALID, "packed records must be 8-byte aligned");
   return submit_impl(c, video_id, n_frames, pts, rec_count, recs, true, first_frame_out);
+}
+
+// Frames whose records already lie in this GPU's memory: appended to the video's frame log like a host submit and
+// scanned IN PLACE by K-A on the context's device stream — no staging, no copy of the records; only the per-frame
+// metadata (8 B offset + 8 B pts per frame) crosses PCIe.
+int mscan_submit_device(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                        const void* d_recs, int packed, void* ready_stream, uint64_t* first_frame_out) try {
+  ApiTimer trace_(c, "mscan_submit_device");
+  if (!c) return MSCAN_ERR_INVALID;
+  if (n_frames && (!pts || !rec_count)) return fail(c, MSCAN_ERR_INVALID, "null pts/rec_count");
+  if (reinterpret_cast<uintptr_t>(d_recs) & 15u) return fail(c, MSCAN_ERR_INVALID, "d_recs must be 16-byte aligned");
+  std::unique_lock<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  auto it = c->videos.find(video_id);
+  if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  Video& v = it->second;
+  const uint64_t vbase = v.n_frames;
+  if (first_frame_out) *first_frame_out = vbase;
+  if (n_frames == 0) return MSCAN_OK;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_frames; ++i) total += rec_count[i];
+  if (total && !d_recs) return fail(c, MSCAN_ERR_INVALID, "null d_recs with non-zero rec_count");
+  if (ready_stream) {  // the records become ready on the producer's stream
+    CU(cudaEventRecord(c->dev_ready, (cudaStream_t)ready_stream));
+    CU(cudaStreamWaitEvent(c->dev_stream, c->dev_ready, 0));
+  }
+  {  // the frames of an open staged segment are contiguous in the log: close it before this call takes log frames
+    int rc = launch_segment(c, c->slabs[c->cur]);
+    if (rc) return rc;
+  }
+  std::vector<uint64_t> off;
+  uint32_t f = 0;
+  uint64_t rec_at = 0;
+  while (f < n_frames) {
+    if (c->log_head >= c->log_limit) {
+      int rc = launch_segment(c, c->slabs[c->cur]);  // (a staged segment's frames must stay contiguous in the log)
+      if (rc) return rc;
+      if (!log_find_space(c)) {
+        v.n_frames = vbase + f;
+        return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos)", (unsigned long long)c->log_cap);
+      }
+    }
+    const uint32_t take = (uint32_t)std::min<uint64_t>(n_frames - f, c->log_limit - c->log_head);
+    off.resize((size_t)take + 1);
+    uint64_t r = rec_at;
+    for (uint32_t i = 0; i < take; ++i) {
+      off[i] = r;  // record indices from d_recs: K-A reads frames at any record offset of a 16-byte aligned base
+      r += rec_count[f + i];
+    }
+    off[take] = r;
+    const uint64_t at = c->log_head;
+    uint64_t* d_off = nullptr;
+    CU(cudaMallocAsync((void**)&d_off, sizeof(uint64_t) * ((size_t)take + 1), c->dev_stream));
+    // pageable sources: both copies are staged by the runtime before the calls return
+    CU(cudaMemcpyAsync(d_off, off.data(), sizeof(uint64_t) * ((size_t)take + 1), cudaMemcpyHostToDevice, c->dev_stream));
+    CU(cudaMemcpyAsync(c->d_pts + at, pts + f, sizeof(double) * take, cudaMemcpyHostToDevice, c->dev_stream));
+    c->a_h2d_bytes.fetch_add(16ull * take + 8, std::memory_order_relaxed);
+    ScanArgs a = base_args(c);
+    a.recs = reinterpret_cast<const uint8_t*>(d_recs);
+    a.packed = packed ? 1u : 0u;
+    a.rec_off = d_off;
+    a.frame_geom = nullptr;            // every frame of the call has the video's geometry:
+    a.geoms = c->d_geoms + v.geom;     // index 0 of a table that starts at it
+    a.flags = c->d_flags + at;
+    a.counts = c->d_counts + at;
+    a.n_frames = take;
+    const ScanPlan& plan = packed ? c->plan_packed : c->plan;
+    a.stages = plan.stages;
+    a.max_cells = plan.cells;
+    a.max_bit_words = plan.bit_words;
+    int rc = run_scan(c, a, plan, c->dev_stream, r - rec_at, kSlabs);
+    CU(cudaFreeAsync(d_off, c->dev_stream));
+    if (rc) {
+      v.n_frames = vbase + f;
+      return rc;
+    }
+    CU(cudaEventRecord(c->dev_done, c->dev_stream));
+    c->dev_seq += 1;
+    v.dev_seq = c->dev_seq;
+    const uint64_t vpos = vbase + f;
+    if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == at && v.extents.back().vpos + v.extents.back().n == vpos)
+      v.extents.back().n += take;
+    else v.extents.push_back(Extent{at, take, vpos});
+    v.n_frames = vpos + take;
+    c->log_head += take;
+    rec_at = r;
+    f += take;
+  }
+  return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
+}
+
+int mscan_device_pci_bus_id(int device, char* buf, int len) {
+  if (!buf || len < 13) return MSCAN_ERR_INVALID;
+  if (cudaDeviceGetPCIBusId(buf, len, device) != cudaSuccess) {
+    cudaGetLastError();
+    buf[0] = 0;
+    return MSCAN_ERR_CUDA;
+  }
+  return MSCAN_OK;
 }
 
 int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out) {
@@ -1902,7 +2058,9 @@ static int scan_device_impl(mscan_ctx* c, const void* d_recs, bool packed, const
   // upload only when the table changed: a pageable-source copy would serialise the stream
   if (c->user_geoms_cached.size() != n_geoms ||
       std::memcmp(c->user_geoms_cached.data(), dg.data(), sizeof(DevGeom) * n_geoms) != 0) {
-    CU(cudaStreamSynchronize(st));
+    // earlier launches on OTHER caller streams may still read the old table: drain the device before rewriting it
+    // (the table only changes when a caller switches geometry sets, so this is rare)
+    CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(c->d_user_geoms, dg.data(), sizeof(DevGeom) * n_geoms, cudaMemcpyHostToDevice));
     c->user_geoms_cached = dg;
   }

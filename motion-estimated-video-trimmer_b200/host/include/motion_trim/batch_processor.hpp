@@ -47,7 +47,7 @@ class BatchProcessor {
   // WATCH_MODE=1 (reference src/batch_processor.cpp:237-305): poll the input directory every 2 s, enqueue
   // files that are new, have no output yet and whose size was stable for 500 ms.
   void monitor_directory(const std::string& input_dir, const std::string& output_dir);
-  void stream_worker(int stream_id, int gpu, const std::string& output_dir);
+  void stream_worker(int stream_id, int gpu, std::vector<int> cpu_set, int threads, const std::string& output_dir);
 
   int streams_per_gpu_;
   GpuPool pool_;

@@ -13,6 +13,7 @@
 
 #include "motion_trim/config.hpp"
 #include "motion_trim/pipeline.hpp"
+#include "motion_trim/system.hpp"
 
 namespace fs = std::filesystem;
 
@@ -91,14 +92,14 @@ void BatchProcessor::monitor_directory(const std::string& input_dir, const std::
   queue_cv_.notify_all();
 }
 
-void BatchProcessor::stream_worker(int stream_id, int gpu, const std::string& output_dir) {
-  int threads = Config::threads_per_stream();
-  if (threads <= 0) threads = std::max(1u, std::thread::hardware_concurrency() / (unsigned)(streams_per_gpu_ * pool_.size()));
+void BatchProcessor::stream_worker(int stream_id, int gpu, std::vector<int> cpu_set, int threads, const std::string& output_dir) {
+  if (pin_thread_to_cpus(cpu_set))  // like src/batch_processor.cpp:307-320: the stream thread lives on its own CPUs
+    std::printf("[INFO] [Stream %d] GPU %d, pinned to CPUs [%s]\n", stream_id, gpu, cpu_list_string(cpu_set).c_str());
   std::string file;
   while (next_file(file)) {
     const std::string out = (fs::path(output_dir) / fs::path(file).filename()).string();
     const auto t0 = std::chrono::steady_clock::now();
-    ProcessingPipeline p(file, out, stream_id, threads);
+    ProcessingPipeline p(file, out, stream_id, threads, cpu_set);
     p.set_gpu(&pool_, gpu);
     p.set_ffmpeg_queue(&ffmpeg_queue_);
     StreamResult r;
@@ -153,7 +154,38 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
     return (int)work_.size();
   }
   const int n_gpus = pool_.size();
-  std::printf("[INFO] %zu files, %d GPU(s), %d stream(s) per GPU\n", work_.size(), n_gpus, streams_per_gpu_);
+  // CPU plan (reference src/batch_processor.cpp:78-110): the CPUs the process may use are dealt to the streams in
+  // disjoint sets of THREADS_PER_STREAM (auto: CPUs / streams); a stream's chunk workers, its projection work and its
+  // FFmpeg job stay on that set. New: a GPU's streams take CPUs local to that GPU first (sysfs local_cpulist), so the
+  // pinned staging they fill is on the GPU's NUMA node; with one set of CPUs for all GPUs this is the reference's plan.
+  const std::vector<int> cpus = get_available_cpus();
+  const int n_streams = n_gpus * streams_per_gpu_;
+  int threads = Config::threads_per_stream();
+  if (threads <= 0) threads = std::max(1, (int)cpus.size() / n_streams);
+  std::vector<std::vector<int>> stream_cpus((size_t)n_streams);
+  {
+    std::set<int> free_cpus(cpus.begin(), cpus.end());
+    for (int g = 0; g < n_gpus; ++g) {
+      char bus[32] = {0};
+      std::vector<int> local;
+      if (mscan_device_pci_bus_id(g, bus, (int)sizeof bus) == MSCAN_OK) local = pci_local_cpus(bus);
+      for (int s = 0; s < streams_per_gpu_; ++s) {
+        std::vector<int>& mine = stream_cpus[(size_t)(g * streams_per_gpu_ + s)];
+        for (int c : local)
+          if ((int)mine.size() < threads && free_cpus.erase(c)) mine.push_back(c);
+        while ((int)mine.size() < threads && !free_cpus.empty()) {  // not enough local ones left: any free CPU
+          mine.push_back(*free_cpus.begin());
+          free_cpus.erase(free_cpus.begin());
+        }
+      }
+    }
+  }
+  // When the streams' chunk workers already occupy every CPU, each worker projects its own chunk on its own CPU; the
+  // library's shared pool (all CPUs per large submit) is for boxes with fewer workers than CPUs.
+  if (n_streams * threads >= (int)cpus.size())
+    for (int g = 0; g < n_gpus; ++g) mscan_set_pack_threads(pool_.ctx(g), 1);
+  std::printf("[INFO] %zu files, %d GPU(s), %d stream(s) per GPU, %d thread(s)/CPU(s) per stream, %zu CPUs available\n", work_.size(), n_gpus,
+              streams_per_gpu_, threads, cpus.size());
   const auto t0 = std::chrono::steady_clock::now();
 
   std::atomic<int> mux_failures{0};
@@ -166,7 +198,8 @@ int BatchProcessor::process(const std::vector<std::string>& input_files, const s
   std::vector<std::thread> streams;
   for (int g = 0; g < n_gpus; ++g)
     for (int s = 0; s < streams_per_gpu_; ++s)
-      streams.emplace_back(&BatchProcessor::stream_worker, this, g * streams_per_gpu_ + s, g, output_dir);
+      streams.emplace_back(&BatchProcessor::stream_worker, this, g * streams_per_gpu_ + s, g, stream_cpus[(size_t)(g * streams_per_gpu_ + s)],
+                           threads, output_dir);
   if (watching_) {  // :161-183 — the monitor feeds the queue until stopped
     std::string input_dir = input_dir_arg;
     if (input_dir.empty() && !input_files.empty()) input_dir = fs::path(input_files[0]).parent_path().string();

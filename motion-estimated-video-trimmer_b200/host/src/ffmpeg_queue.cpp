@@ -2,9 +2,12 @@
 // src/ffmpeg_executor.cpp:24-118; see ffmpeg_queue.hpp).
 #include "motion_trim/ffmpeg_queue.hpp"
 
+#include <spawn.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
 #include <unistd.h>
 
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <filesystem>
@@ -45,7 +48,12 @@ std::string build_concat_list(const std::string& input_path, const std::vector<T
   char line[64];
   for (const TimeSegment& s : segments) {
     if (s.end <= s.start) continue;
-    out += "file '" + abs + "'\n";
+    out += "file '";
+    for (char ch : abs) {  // the concat demuxer's quoting: a single quote inside '...' is written '\''
+      if (ch == '\'') out += "'\\''";
+      else out += ch;
+    }
+    out += "'\n";
     std::snprintf(line, sizeof line, "inpoint %.2f\n", s.start);
     out += line;
     std::snprintf(line, sizeof line, "outpoint %.2f\n", s.end);
@@ -78,15 +86,31 @@ int execute_ffmpeg_cut(const std::string& input_path, const std::string& output_
     std::printf("[WARN] no ffmpeg binary in this image: wrote %s instead of cutting\n", list_path.c_str());
     return 0;
   }
-  std::string cmd;
+  // Same command line as the reference (src/ffmpeg_executor.cpp:60-100: taskset -c <cpus> ffmpeg -f concat … -c copy),
+  // but spawned with an argv vector instead of through a shell: file names are data (watch mode feeds arbitrary
+  // directory entries), so quotes, $(…) or backticks in them must never be interpreted.
+  std::vector<std::string> args;
   if (!cpu_set.empty()) {
-    cmd = "taskset -c ";
-    for (size_t i = 0; i < cpu_set.size(); ++i) cmd += (i ? "," : "") + std::to_string(cpu_set[i]);
-    cmd += " ";
+    std::string cpus;
+    for (size_t i = 0; i < cpu_set.size(); ++i) cpus += (i ? "," : "") + std::to_string(cpu_set[i]);
+    args = {"taskset", "-c", cpus};
   }
-  cmd += ffmpeg + " -y -hide_banner -loglevel error -f concat -safe 0 -i \"" + list_path +
-         "\" -c copy -fflags +genpts -avoid_negative_ts make_zero -movflags +faststart \"" + output_path + "\"";
-  const int status = std::system(cmd.c_str());
+  args.push_back(ffmpeg);
+  for (const char* a : {"-y", "-hide_banner", "-loglevel", "error", "-f", "concat", "-safe", "0", "-i"}) args.push_back(a);
+  args.push_back(list_path);
+  for (const char* a : {"-c", "copy", "-fflags", "+genpts", "-avoid_negative_ts", "make_zero", "-movflags", "+faststart"}) args.push_back(a);
+  args.push_back(output_path);
+  std::vector<char*> argv;
+  for (std::string& a : args) argv.push_back(a.data());
+  argv.push_back(nullptr);
+  pid_t pid = 0;
+  int status = -1;
+  if (posix_spawnp(&pid, argv[0], nullptr, nullptr, argv.data(), environ) == 0) {
+    int st = 0;
+    while (waitpid(pid, &st, 0) < 0 && errno == EINTR) {
+    }
+    status = WIFEXITED(st) ? WEXITSTATUS(st) : -1;
+  }
   std::remove(list_path.c_str());
   if (status != 0) std::printf("[ERROR] FFmpeg failed with status %d\n", status);
   return status;

@@ -13,13 +13,13 @@ GpuPool::~GpuPool() {
 }
 
 bool GpuPool::open(int max_gpus) {
-  int rc = mscan_params_from_env(&params_);
-  if (rc != MSCAN_OK) {
+  if (!Config::validate()) {
     error_ = "unparsable motion_trim environment knob";
     return false;
   }
+  params_ = Config::scan_params();
   int n = 0;
-  rc = mscan_device_count(&n);
+  int rc = mscan_device_count(&n);
   if (rc != MSCAN_OK || n <= 0) {
     error_ = "no CUDA device (libmotionscan has no CPU fallback)";
     return false;
@@ -42,10 +42,7 @@ bool GpuPool::open(int max_gpus) {
     }
   }
   ctx_ = made;
-  // the contexts' projection pools share the host: cores / GPUs threads each (a pool per context sized for the
-  // whole box would oversubscribe it n-fold)
-  const unsigned cores = std::max(1u, std::thread::hardware_concurrency());
-  for (mscan_ctx* c : ctx_) mscan_set_pack_threads(c, (int)std::max(1u, cores / (unsigned)ctx_.size()));
+  // (the library's projection pool is one per process, shared by these contexts: nothing to size per GPU)
   return true;
 }
 

@@ -41,6 +41,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   const std::string input = pos[0], output = pos[1];
+  if (!Config::validate()) return 2;  // an unparsable knob is fatal (the reference's std::stod/stoi terminate)
   if (fs::is_directory(input)) {
     std::vector<std::string> files;
     for (const auto& e : fs::directory_iterator(input))

@@ -78,9 +78,13 @@ bool MvsView::parse(const MappedFile& file) {
   MvsHeader h;
   std::memcpy(&h, file.data(), sizeof h);
   if (std::memcmp(h.magic, MVS_MAGIC, 8) != 0) return false;
+  // the header is untrusted (watch mode picks files up on its own): every bound is checked without arithmetic that
+  // could wrap — a crafted n_records / first_record must not let a submit read or DMA outside the mapping
+  const uint64_t fsize = file.size();
+  if ((uint64_t)h.n_frames > (fsize - sizeof(MvsHeader)) / sizeof(MvsFrameEntry)) return false;
   const uint64_t table_end = sizeof(MvsHeader) + (uint64_t)h.n_frames * sizeof(MvsFrameEntry);
-  if (table_end > file.size() || h.records_offset < table_end || (h.records_offset & 7u)) return false;
-  if (h.records_offset + h.n_records * sizeof(mscan_mv) > file.size()) return false;
+  if (h.records_offset < table_end || h.records_offset > fsize || (h.records_offset & 7u)) return false;
+  if (h.n_records > (fsize - h.records_offset) / sizeof(mscan_mv)) return false;
   if (h.tb_den == 0 || h.fps_den == 0) return false;
   width = h.width;
   height = h.height;
@@ -94,7 +98,7 @@ bool MvsView::parse(const MappedFile& file) {
   frames = reinterpret_cast<const MvsFrame*>(file.data() + sizeof(MvsHeader));
   records = reinterpret_cast<const mscan_mv*>(file.data() + h.records_offset);
   for (uint32_t i = 0; i < n_frames; ++i)  // every frame's records must lie inside the file
-    if (frames[i].first_record + frames[i].n_records > n_records) return false;
+    if (frames[i].first_record > n_records || frames[i].n_records > n_records - frames[i].first_record) return false;
   return true;
 }
 

@@ -17,6 +17,7 @@
 #include "motion_trim/config.hpp"
 #include "motion_trim/gpu_pool.hpp"
 #include "motion_trim/motion_scanner.hpp"
+#include "motion_trim/system.hpp"
 
 namespace motion_trim {
 
@@ -145,6 +146,7 @@ int ProcessingPipeline::run() {
   std::vector<std::thread> workers;
   for (int w = 0; w < n_threads; ++w)
     workers.emplace_back([&, w] {
+      if (!cpu_set_.empty()) pin_thread_to_cpus(cpu_set_);  // src/pipeline.cpp:191-193
       MotionScanner scanner(file_buffer_, pool_->ctx(gpus_[(size_t)w % n_gpus]), video_id);
       if (!scanner.initialize()) {
         failed = true;

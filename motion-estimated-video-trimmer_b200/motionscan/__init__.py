@@ -143,6 +143,8 @@ SYMBOLS = {
     "mscan_video_open_geometry": (_i, [_vp, _u32, _P(Geometry)]),
     "mscan_submit": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _P(_u64)]),
     "mscan_submit_packed": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _P(_u64)]),
+    "mscan_submit_device": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _i, _vp, _P(_u64)]),
+    "mscan_device_pci_bus_id": (_i, [_i, C.c_char_p, _i]),
     "mscan_pack_records": (_i, [_vp, _u64, _vp]),
     "mscan_set_staging_mode": (_i, [_vp, _i]),
     "mscan_set_pack_threads": (_i, [_vp, _i]),
@@ -324,6 +326,13 @@ class Context:
         n = len(rec_count)
         first = C.c_uint64()
         self._ck(self.L.mscan_submit_packed(self.h, vid, n, _ptr(pts), _ptr(rec_count), _ptr(recs8), C.byref(first)))
+        return first.value
+
+    def submit_device(self, vid: int, pts, rec_count, d_recs: int, packed: bool = False, ready_stream: int = 0) -> int:
+        """Frames whose records already lie in this GPU's memory (device pointer d_recs): scanned in place."""
+        n = len(rec_count)
+        first = C.c_uint64()
+        self._ck(self.L.mscan_submit_device(self.h, vid, n, _ptr(pts), _ptr(rec_count), d_recs, int(packed), ready_stream or None, C.byref(first)))
         return first.value
 
     def submit_packed_raw(self, vid: int, n_frames: int, pts_ptr: int, cnt_ptr: int, recs_ptr: int):

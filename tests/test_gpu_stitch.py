@@ -102,6 +102,55 @@ def test_cli_split_one_video_over_gpus():
             assert np.array(segs).reshape(-1, 2).tobytes() == e["segs"].tobytes()
 
 
+def test_cli_batch_identical_on_one_and_two_gpus():
+    """a 16-clip batch sharded by video over 2 GPUs (PARALLEL_STREAMS stream threads per GPU,
+    one context per GPU, no exchange) gives, per video, exactly what one GPU gives — and what the oracle gives."""
+    if n_devices() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import motionscan as ms
+    import oracle_lib as orc
+    from motionscan import mvs_io
+
+    p = cases()["batchclip_seed100"].params
+    n_clips, n_frames = 16, 450
+    want = {}
+    with tempfile.TemporaryDirectory() as d:
+        ind = Path(d) / "in"
+        ind.mkdir()
+        for k in range(n_clips):
+            spec = ms.synth_preset(3, 500 + k)
+            cnt, off, recs, pts = ms.synth_host(spec, 0, n_frames)
+            mvs_io.write_mvs(ind / f"clip{k:02d}.mvs", spec.width, spec.height, 30, 1, np.arange(n_frames), cnt, recs)
+            gw, gh, m = orc.geometry(spec.width, spec.height, p.block_size, p.block_shift, p.vertical_mask)
+            of, _ = orc.scan_frames(orc.make_cfg(p, gw, gh, m), recs, off, threads=4)
+            _, ores = orc.video_tail(pts, of, n_frames / 30.0, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
+            want[f"clip{k:02d}"] = (ores.decision, ores.saved_pct)
+        runs = {}
+        for gpus in (1, 2):
+            outd = Path(d) / f"out{gpus}"
+            r = run_cli(["--print-segments", str(ind), str(outd)], p, chunk_sec=5.0,
+                        extra_env={"PARALLEL_STREAMS": "2", "MOTION_TRIM_GPUS": str(gpus)})
+            assert r.returncode == 0, r.stdout + r.stderr
+            assert f"{gpus} GPU(s)" in r.stdout
+            got = {}
+            for line in r.stdout.splitlines():
+                if line.startswith("RESULT "):
+                    parts = line.split()
+                    kv = dict(x.split("=") for x in parts[2:])
+                    got[parts[1][:-4]] = (kv["rc"], kv["decision"], kv["segments"], kv["saved_pct"], kv["gpu"])
+            runs[gpus] = got
+            lists = {f.name: f.read_text().replace(str(ind.resolve()), "IN") for f in sorted(outd.glob("*.concat.txt"))}
+            runs[(gpus, "lists")] = lists
+        assert sorted(runs[1]) == sorted(runs[2]) == sorted(want)
+        assert {v[4] for v in runs[2].values()} == {"0", "1"}, "both GPUs must have scanned videos"
+        for name in want:
+            assert runs[1][name][:4] == runs[2][name][:4], name                      # identical per-video results
+            assert int(runs[1][name][1]) == want[name][0]                            # and the oracle's decision
+            if want[name][0]:
+                assert float.fromhex(runs[1][name][3]) == want[name][1], name
+        assert runs[(1, "lists")] == runs[(2, "lists")]                              # identical cut lists (segments)
+
+
 def test_cli_watch_mode_picks_up_new_files():
     """WATCH_MODE=1 (batch_processor.cpp:237-305): files that appear later are processed; outputs that exist are
     skipped; MOTION_TRIM_WATCH_IDLE_EXIT_SEC ends the loop (the reference's never ends)."""

@@ -116,3 +116,68 @@ def test_cli_batch_directory_matches_reference():
             else:
                 assert not (outd / f"{n}.mvs.concat.txt").exists()
         assert "BATCH SUMMARY" in r.stdout
+
+
+def test_unparsable_knob_is_fatal_before_anything_runs(tmp_path):
+    """One parser for the scan knobs (the library's): garbage in the environment ends the program with a message, like
+    the reference's std::stod/stoi (include/motion_trim/config.hpp:28-53) — it does not fall back to a default."""
+    c = cases()["kat_seg_S1"]
+    path = tmp_path / "x.mvs"
+    write_case(c, path)
+    for knob in ("MV_THRESHOLD_SQ", "VERTICAL_MASK", "CHUNK_DURATION_SEC", "PARALLEL_STREAMS"):
+        r = run_cli([str(path), str(tmp_path / "out.mp4")], c.params, extra_env={knob: "abc"})
+        assert r.returncode == 2, (knob, r.stdout, r.stderr)
+        assert "[ERROR]" in r.stderr
+
+
+def test_concat_list_escapes_single_quotes(tmp_path):
+    """File names are data: a single quote in the input path is written in the concat demuxer's own quoting."""
+    src = tmp_path / "t.cpp"
+    src.write_text(r"""
+#include <cstdio>
+#include "motion_trim/ffmpeg_queue.hpp"
+int main() {
+  std::vector<motion_trim::TimeSegment> s{{1.0, 2.5}, {3.0, 3.0}};
+  std::fputs(motion_trim::build_concat_list("/data/it's here/a.mp4", s).c_str(), stdout);
+}
+""")
+    exe = tmp_path / "t"
+    subprocess.run(["g++", "-std=c++17", "-I", str(HOST / "include"), "-I", str(ROOT / "include"), "-o", str(exe), str(src),
+                    str(HOST / "src" / "ffmpeg_queue.cpp"), "-pthread"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert out == "file '/data/it'\\''s here/a.mp4'\ninpoint 1.00\noutpoint 2.50\n"
+
+
+@pytest.mark.gpu
+def test_crafted_stream_headers_are_rejected(tmp_path):
+    """An MVS1 header whose counts would wrap the bounds arithmetic must be refused (watch mode opens whatever appears
+    in the directory), not read or DMA'd out of bounds."""
+    import struct
+
+    c = cases()["kat_seg_S1"]
+    good = tmp_path / "good.mvs"
+    write_case(c, good)
+    raw = bytearray(good.read_bytes())
+    hdr = list(mvs_io.HDR.unpack_from(raw, 0))
+    names = ["magic", "width", "height", "tb_num", "tb_den", "fps_num", "fps_den", "duration_us", "n_frames", "flags", "records_offset", "n_records"]
+    idx = {n: i for i, n in enumerate(names)}
+    attacks = {
+        "n_records_wraps": {"n_records": (1 << 64) // 40 + 3},
+        "records_offset_huge": {"records_offset": (1 << 64) - 40},
+        "n_frames_huge": {"n_frames": 0xFFFFFFFF},
+    }
+    for name, patch in attacks.items():
+        h = list(hdr)
+        for k, v in patch.items():
+            h[idx[k]] = v
+        bad = tmp_path / f"{name}.mvs"
+        bad.write_bytes(mvs_io.HDR.pack(*h) + bytes(raw[mvs_io.HDR.size:]))
+        r = run_cli([str(bad), str(tmp_path / "o.mp4")], c.params)
+        assert r.returncode == 1 and "Failed to initialize probe" in r.stdout, (name, r.stdout, r.stderr)
+    # a frame entry pointing past the records
+    fr = np.frombuffer(bytes(raw[mvs_io.HDR.size : mvs_io.HDR.size + 24 * hdr[idx["n_frames"]]]), dtype=mvs_io.FRAME_DTYPE).copy()
+    fr["first_record"][-1] = (1 << 64) - 2
+    bad = tmp_path / "frame_wraps.mvs"
+    bad.write_bytes(bytes(raw[: mvs_io.HDR.size]) + fr.tobytes() + bytes(raw[mvs_io.HDR.size + fr.nbytes :]))
+    r = run_cli([str(bad), str(tmp_path / "o.mp4")], c.params)
+    assert r.returncode == 1 and "Failed to initialize probe" in r.stdout
