@@ -123,6 +123,7 @@ def test_cli_batch_identical_on_one_and_two_gpus():
             mvs_io.write_mvs(ind / f"clip{k:02d}.mvs", spec.width, spec.height, 30, 1, np.arange(n_frames), cnt, recs)
             gw, gh, m = orc.geometry(spec.width, spec.height, p.block_size, p.block_shift, p.vertical_mask)
             of, _ = orc.scan_frames(orc.make_cfg(p, gw, gh, m), recs, off, threads=4)
+            pts = np.arange(n_frames, dtype=np.float64) * (1.0 / 30.0)  # ticks * time_base, as the host computes it (:361)
             _, ores = orc.video_tail(pts, of, n_frames / 30.0, p.max_gap_sec, p.padding_sec, p.min_savings_pct)
             want[f"clip{k:02d}"] = (ores.decision, ores.saved_pct)
         runs = {}
