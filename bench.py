@@ -543,10 +543,10 @@ def run_gpu(args):
     #                   worker pool projects them (bound by reading 40 B/record from DRAM)
     #   packed_pinned   the caller hands over records it projected itself beforehand; only DMA + kernels are timed
     # `e2e.value` is the best of the modes that start from native host records (the first three).
-    e2e_target = args.e2e_records / world if strong else args.e2e_records
-    e2e_frames = int(min(max(np.searchsorted(off, np.uint64(int(e2e_target)), side="right") - 1, 1), n_frames))
-    if args.e2e_frames:
-        e2e_frames = min(args.e2e_frames, n_frames)
+    # the same frame count the reference arm derives (sample_frames): both arms scan the same host sample
+    e2e_frames = min(sample_frames(args, spec, ms, max(1, len(my_cpus))), n_frames)
+    if strong:
+        e2e_frames = max(1, e2e_frames // world)
     e_rec = int(off[e2e_frames])
     h_recs = ctx.pinned_array(e_rec, ms.MV_DTYPE)
     h_r8 = ctx.pinned_array(e_rec, ms.MV8_DTYPE)

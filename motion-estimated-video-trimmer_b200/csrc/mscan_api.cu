@@ -1257,8 +1257,8 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
   if (kind == kFillProject) {
     const auto t0 = std::chrono::steady_clock::now();
     uint64_t* to = reinterpret_cast<uint64_t*>(s.h_recs + off);
-    PackPool* pool = n_recs >= kPoolMinRecs ? shared_pool() : nullptr;
-    if (pool && pool->workers() > 0 && c->pack_threads != 1) pool->run(from, to, n_recs, c->pack_threads);
+    PackPool* pool = (n_recs > kPoolMinRecs && c->pack_threads != 1) ? shared_pool() : nullptr;
+    if (pool && pool->workers() > 0) pool->run(from, to, n_recs, c->pack_threads);
     else project_records(from, n_recs, to);
     c->a_project_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
                               std::memory_order_relaxed);
@@ -1305,9 +1305,9 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   const uint64_t in_stride = src_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
   // is the source pinned? (before taking the mutex; see PinnedRanges)
   bool pinned = false;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < n_frames; ++i) total += rec_count[i];
   if (recs) {
-    uint64_t total = 0;
-    for (uint32_t i = 0; i < n_frames; ++i) total += rec_count[i];
     const uint64_t src_bytes = total * in_stride;
     if (src_bytes) {
       pinned = pinned_ranges().contains(recs, src_bytes);
@@ -1349,8 +1349,12 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   const bool staged = project || !pinned;
   const FillKind kind = project ? kFillProject : (pinned ? kFillInPlace : kFillMemcpy);
   const uint64_t out_stride = slab_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
-  // large projected submits go out in sub-batches, so the copy of one overlaps the projection of the next
-  const uint64_t max_take_recs = project ? (4ull << 20) : ~0ull;
+  // Large projected submits go out in pieces. A piece is what one reservation's writer holds while it projects, and a
+  // slab's launch waits for its writers: when the calling thread projects alone (pool off, or several decode workers
+  // each feeding whole chunks) pieces stay small — 256 Ki records ≈ 1 ms — so that a slab flip never waits long for a
+  // neighbour; a pool job (all the process's cores on one piece) takes 4 Mi records at a time.
+  const bool pool_job = project && total > kPoolMinRecs && c->pack_threads != 1 && shared_pool() && shared_pool()->workers() > 0;
+  const uint64_t max_take_recs = project ? (pool_job ? (4ull << 20) : kPoolMinRecs) : (src_packed && !pinned ? (1ull << 20) : ~0ull);
   uint32_t f = 0;
   uint64_t src_rec = 0;
   int result = MSCAN_OK;

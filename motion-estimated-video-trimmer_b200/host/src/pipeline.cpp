@@ -94,8 +94,12 @@ int ProcessingPipeline::run() {
   // refuses (or MOTION_TRIM_NO_PIN is set) submits fall back to the library's pinned staging copy.
   bool registered = false;
   // (decode-fed runs stage projected records instead: nothing is DMA'd out of the media file)
-  if (!decode_fed && !std::getenv("MOTION_TRIM_NO_PIN"))
+  if (!decode_fed && !std::getenv("MOTION_TRIM_NO_PIN")) {
     registered = mscan_host_register(gpu, const_cast<uint8_t*>(file_buffer_.data()), file_buffer_.size(), 1) == MSCAN_OK;
+    static std::atomic<bool> told{false};
+    if (!registered && !told.exchange(true))
+      logf(stream_id_, "[INFO] ", std::string("input mapping not pinned (") + mscan_last_error(gpu) + "): records are projected into the library's pinned ring instead");
+  }
   lap(phases_.pin);
   std::vector<mscan_ctx*> readers;  // every context that may DMA out of the mapping
   for (int g : gpus_) readers.push_back(pool_->ctx(g));

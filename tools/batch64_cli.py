@@ -37,7 +37,10 @@ def main():
     ap.add_argument("--gpus", default="1,2,4,8")
     ap.add_argument("--streams", type=int, default=2, help="PARALLEL_STREAMS per GPU (shipped env: 2)")
     ap.add_argument("--keep", action="store_true")
-    ap.add_argument("--modes", default="default,populate")
+    ap.add_argument("--modes", default="default,nopin")
+    ap.add_argument("--chunk", default="10", help="CHUNK_DURATION_SEC (comma list: one run per value)")
+    ap.add_argument("--threads", default="0", help="THREADS_PER_STREAM (0 = auto: CPUs / streams, like the reference; comma list)")
+    ap.add_argument("--trace", action="store_true", help="MSCAN_TRACE=1: print the library's per-entry-point wall times of each run")
     args = ap.parse_args()
     import ctypes as C
 
@@ -52,12 +55,18 @@ def main():
         mvs_io.write_mvs(ind / f"clip{k:03d}.mvs", spec.width, spec.height, int(spec.fps), 1, np.arange(args.frames), cnt, recs)
         n_rec += int(off[-1])
     print(f"# generated {args.clips} clips x {args.frames} frames = {n_rec} records ({n_rec * 40 / 1e9:.1f} GB) in {time.time() - t0:.1f} s", flush=True)
-    env0 = dict(os.environ, MV_THRESHOLD_SQ="4.0", VECTORS_NEEDED="4", CLUSTERS_NEEDED="2", VERTICAL_MASK="0.05", MAX_GAP_SEC="5",
-                PADDING_SEC="0.5", MIN_SAVINGS_PCT="5", CHUNK_DURATION_SEC="60", TARGET_FPS="0", THREADS_PER_STREAM="1",
-                PARALLEL_STREAMS=str(args.streams))
     baseline = None
-    for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)]:
-        for mode, extra in (("default", {}), ("populate", {"MOTION_TRIM_POPULATE": "1"})):
+    combos = [(g, t, c) for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)] for t in args.threads.split(",")
+              for c in args.chunk.split(",")]
+    for g, thr, chunk in combos:
+        env0 = dict(os.environ, MV_THRESHOLD_SQ="4.0", VECTORS_NEEDED="4", CLUSTERS_NEEDED="2", VERTICAL_MASK="0.05", MAX_GAP_SEC="5",
+                    PADDING_SEC="0.5", MIN_SAVINGS_PCT="5", CHUNK_DURATION_SEC=chunk, TARGET_FPS="0", THREADS_PER_STREAM=thr,
+                    PARALLEL_STREAMS=str(args.streams))
+        if args.trace:
+            env0["MSCAN_TRACE"] = "1"
+        # default: the mapped file is pinned and DMA'd in place (40 B/record over PCIe, no host pass); nopin: the chunk
+        # workers project their chunks into the library's pinned ring (8 B/record over PCIe); populate: MAP_POPULATE
+        for mode, extra in (("default", {}), ("nopin", {"MOTION_TRIM_NO_PIN": "1"}), ("populate", {"MOTION_TRIM_POPULATE": "1"})):
             if mode not in args.modes.split(","):
                 continue
             outd = Path(args.dir) / f"out_{g}_{mode}"
@@ -73,7 +82,9 @@ def main():
             if baseline is None:
                 baseline = dec
             ph = re.search(r"phases \(sum over files, s\): (.*)", r.stdout)
-            print(json.dumps({"gpus": g, "feed": mode, "phases": ph.group(1) if ph else None, "streams_per_gpu": args.streams, "rc": r.returncode, "files": len(res),
+            if args.trace:
+                print("\n".join(ln for ln in r.stderr.splitlines() if "mscan trace" in ln), flush=True)
+            print(json.dumps({"gpus": g, "feed": mode, "threads_per_stream": thr, "chunk_sec": chunk, "phases": ph.group(1) if ph else None, "streams_per_gpu": args.streams, "rc": r.returncode, "files": len(res),
                               "batch_wall_s": scan_wall, "process_wall_s": round(wall, 3), "records_per_s": n_rec / scan_wall,
                               "same_results_as_first_run": dec == baseline}), flush=True)
     if not args.keep:
