@@ -90,7 +90,12 @@ enum {
   MSCAN_STAGING_AUTO = 0,  /* pinned source: DMA the native records in place (no host pass);
                               pageable source: the staging pass projects to mscan_mv8 (default)  */
   MSCAN_STAGING_PACK = 1,  /* always project on the host, even from pinned memory                */
-  MSCAN_STAGING_NATIVE = 2 /* never project: pageable sources are memcpy'd as 40-byte records    */
+  MSCAN_STAGING_NATIVE = 2, /* never project: pageable sources are memcpy'd as 40-byte records   */
+  MSCAN_STAGING_ELIDE = 3   /* project, and send static macroblocks (src == dst, ~90 % of a CCTV stream) as their 4 dst
+                               bytes + a mask bit: a lossless transport form of the mscan_mv8 sequence that the kernel
+                               expands again (≈ 4.6 B/record over PCIe at 10 % moving records). The calling thread does
+                               the encoding — made for decode threads submitting their own frames. Grids beyond one
+                               CTA's shared memory (8K and larger) are sent as mscan_mv8 instead. */
 };
 
 /* ---- TimeSegment (include/motion_trim/types.hpp:56-59) ----------------- */
@@ -147,6 +152,8 @@ typedef struct mscan_stats {
   uint64_t records_projected; /* native records the staging pass projected to mscan_mv8  */
   double project_ms;          /* host wall time spent in that projection                 */
   uint64_t peer_bytes;        /* bytes mscan_video_append_from copied in from other contexts */
+  uint64_t records_elided;    /* records sent in the static-elided form (MSCAN_STAGING_ELIDE)   */
+  uint64_t elided_bytes;      /* … and the bytes they took                                      */
 } mscan_stats;
 
 typedef struct mscan_ctx mscan_ctx;
@@ -218,6 +225,19 @@ int mscan_submit_device(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, co
 /* The projection itself, usable from any thread without a context or a GPU: out[i] = bytes 6..13 of
  * recs[i]. out must be 8-byte aligned; written with streaming stores (it is read next by the DMA engine). */
 int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out);
+/* The static-elided transport form itself (what MSCAN_STAGING_ELIDE puts on the wire), usable without a context or a
+ * GPU — ONE frame of n native records. The frame is cut into tiles of 1024 records (the last one shorter), tiles follow
+ * each other 16-byte aligned; a tile is
+ *     hdr : {uint32 mask, uint32 base} per block of 32 records — bit i of mask: record i of the block is moving
+ *           (src != dst); base: index of the block's first entry in `src` — padded to 16 bytes
+ *     dst : uint32 per record (dst_x | dst_y << 16), padded to 16 bytes
+ *     src : uint32 per MOVING record (src_x | src_y << 16), in record order, padded to 16 bytes
+ * i.e. exactly bytes 6..13 of every record (src/motion_scanner.cpp:243-256 reads nothing else), with the src half
+ * dropped where it repeats the dst half; no arithmetic of the path. out: 16-byte aligned, cap >= mscan_elide_bound(n);
+ * tile_end16[t]: end of tile t in 16-byte units from out (tile_cap >= ceil(n / 1024)); bytes_out: bytes written. */
+int mscan_elide_records(const mscan_mv* recs, uint32_t n, void* out, size_t cap, uint32_t* tile_end16, uint32_t tile_cap,
+                        size_t* bytes_out);
+size_t mscan_elide_bound(uint32_t n);
 /* MSCAN_STAGING_*; default AUTO. */
 int mscan_set_staging_mode(mscan_ctx* ctx, int mode);
 /* Threads (including the caller) that project one large submit; 0 → as many as the process may run on

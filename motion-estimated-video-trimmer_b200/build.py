@@ -20,7 +20,7 @@ FEED_SRC = CSRC / "feed_harness.cpp"
 
 SOURCES = ["ka_scan.cu", "ka_scan_cluster.cu", "kc_segments.cu", "synth.cu", "synth_host.cu", "mscan_api.cu"]
 HOST_SOURCES = ["host_project.cpp"]  # plain C++ (g++): host SIMD paths selected at run time
-HOST_CXXFLAGS = ["-O3", "-std=c++17", "-march=x86-64-v3", "-fPIC", "-Wall", "-Wextra"]
+HOST_CXXFLAGS = ["-O3", "-std=c++17", "-march=x86-64-v3", "-fPIC", "-Wall", "-Wextra", "-I/usr/local/cuda/include"]
 HEADERS = [CSRC / "common.cuh", CSRC / "kernels.cuh", ROOT / "include" / "motionscan.h", ROOT / "include" / "mvgen_core.h"]
 
 NVCC_FLAGS = [

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "kernels.cuh"
+
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -143,6 +145,178 @@ void project_records(const uint8_t* in, uint64_t n, uint64_t* out) {
 #if defined(__x86_64__)
   if (stream) _mm_sfence();
 #endif
+}
+
+}  // namespace mscan
+
+// ---- mvz: the projected records with static macroblocks elided ---------------------------------------------------
+// A lossless transport form of the mscan_mv8 sequence: a record whose src equals its dst — a static
+// macroblock, ~90 % of a CCTV stream — is sent as its 4 dst bytes plus one mask bit; a moving record as dst + src.
+// The kernel rebuilds exactly the 8 bytes per record the path reads, so nothing of the path's arithmetic runs here:
+// the only operation on the data is a byte-equality test used to choose the encoding.
+//
+// A frame is cut into tiles of kMvzTileRecs records (the last one shorter); a tile is
+//     hdr  : one {u32 mask, u32 base} per block of 32 records (bit i of mask: record i of the block is moving;
+//            base: index of the block's first entry in `src`), padded to 16 bytes
+//     dst  : u32 per record (dst_x | dst_y << 16), padded to 16 bytes
+//     src  : u32 per MOVING record (src_x | src_y << 16), in record order, padded to 16 bytes
+// and tiles follow each other 16-byte aligned. tile_end16[t] receives the end offset of tile t in 16-byte units,
+// relative to `out`.
+namespace mscan {
+
+namespace {
+
+inline uint32_t round16(uint32_t b) { return (b + 15u) & ~15u; }
+
+// One tile, portable version.
+uint32_t mvz_tile_scalar(const uint8_t* in, uint32_t n, uint8_t* out) {
+  const uint32_t nb = (n + 31u) >> 5;
+  const uint32_t hdr_bytes = round16(8u * nb), dst_bytes = round16(4u * n);
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(out);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + hdr_bytes);
+  uint32_t* src = reinterpret_cast<uint32_t*>(out + hdr_bytes + dst_bytes);
+  uint32_t m = 0;
+  for (uint32_t b = 0; b < nb; ++b) {
+    const uint32_t r0 = b * 32u, r1 = r0 + 32u < n ? r0 + 32u : n;
+    uint32_t mask = 0;
+    const uint32_t base = m;
+    for (uint32_t r = r0; r < r1; ++r) {
+      uint64_t v;
+      memcpy(&v, in + (size_t)kRec * r + 6, sizeof v);
+      const uint32_t s = (uint32_t)v, d = (uint32_t)(v >> 32);
+      dst[r] = d;
+      src[m] = s;
+      const uint32_t mov = s != d;
+      m += mov;
+      mask |= mov << (r - r0);
+    }
+    hdr[2 * b] = mask;
+    hdr[2 * b + 1] = base;
+  }
+  for (uint32_t i = 2 * nb; i < hdr_bytes / 4; ++i) hdr[i] = 0;
+  for (uint32_t i = n; i < dst_bytes / 4; ++i) dst[i] = 0;
+  const uint32_t src_bytes = round16(4u * m);
+  for (uint32_t i = m; i < src_bytes / 4; ++i) src[i] = 0;
+  return hdr_bytes + dst_bytes + src_bytes;
+}
+
+#if defined(__x86_64__)
+// One tile with AVX-512 VBMI: 16 records per step — two of the projection's 8-record byte gathers, a dword
+// de-interleave into 16 src / 16 dst, one compare, one compress.
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) uint32_t mvz_tile_vbmi(const uint8_t* in, uint32_t n, uint8_t* out) {
+  const uint32_t nb = (n + 31u) >> 5;
+  const uint32_t hdr_bytes = round16(8u * nb), dst_bytes = round16(4u * n);
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(out);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(out + hdr_bytes);
+  uint32_t* src = reinterpret_cast<uint32_t*>(out + hdr_bytes + dst_bytes);
+  const Tables& t = tables();
+  const __m512i ia = _mm512_load_si512(t.a), ib = _mm512_load_si512(t.b), ic = _mm512_load_si512(t.c);
+  const __mmask64 mb = t.mask_b, mc = t.mask_c;
+  const __m512i even = _mm512_set_epi32(30, 28, 26, 24, 22, 20, 18, 16, 14, 12, 10, 8, 6, 4, 2, 0);
+  const __m512i odd = _mm512_set_epi32(31, 29, 27, 25, 23, 21, 19, 17, 15, 13, 11, 9, 7, 5, 3, 1);
+#define MVZ_GATHER8(out, p)                                                                                          \
+  do {                                                                                                               \
+    const __m512i z0_ = _mm512_loadu_si512(p), z1_ = _mm512_loadu_si512((p) + 64), z2_ = _mm512_loadu_si512((p) + 128), \
+                  z3_ = _mm512_loadu_si512((p) + 192), z4_ = _mm512_loadu_si512((p) + 256);                           \
+    __m512i v_ = _mm512_permutex2var_epi8(z0_, ia, z1_);                                                             \
+    v_ = _mm512_mask_mov_epi8(v_, mb, _mm512_permutex2var_epi8(z2_, ib, z3_));                                       \
+    out = _mm512_mask_permutexvar_epi8(v_, mc, ic, z4_);                                                             \
+  } while (0)
+  uint32_t m = 0;
+  const uint32_t full16 = n / 16u;  // steps of 16 whole records
+  uint32_t mask = 0, base = 0;
+  for (uint32_t g = 0; g < full16; ++g) {
+    const uint8_t* p = in + (size_t)640 * g;
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 128), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 256), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 384), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 512), _MM_HINT_T0);
+    __m512i q0, q1;  // 2 x 8 records: src | dst << 32
+    MVZ_GATHER8(q0, p);
+    MVZ_GATHER8(q1, p + 320);
+    const __m512i s = _mm512_permutex2var_epi32(q0, even, q1);  // 16 src dwords
+    const __m512i d = _mm512_permutex2var_epi32(q0, odd, q1);   // 16 dst dwords
+    const __mmask16 k = _mm512_cmpneq_epi32_mask(s, d);
+    _mm512_storeu_si512(dst + 16 * g, d);
+    _mm512_storeu_si512(src + m, _mm512_maskz_compress_epi32(k, s));  // (writes 64 bytes; the next store overlaps the slack)
+    if ((g & 1u) == 0) {
+      base = m;
+      mask = (uint32_t)k;
+    } else {
+      hdr[g - 1] = mask | ((uint32_t)k << 16);  // block b = g / 2: words 2b, 2b + 1
+      hdr[g] = base;
+    }
+    m += (uint32_t)__builtin_popcount((unsigned)k);
+  }
+  // the remaining (< 16) records, and the header of a block whose second half they are
+  uint32_t r = full16 * 16u;
+  if (r < n || (full16 & 1u)) {
+    if ((full16 & 1u) == 0) {
+      base = m;
+      mask = 0;
+    }
+    const uint32_t b = r >> 5;
+    for (; r < n; ++r) {
+      uint64_t v;
+      memcpy(&v, in + (size_t)kRec * r + 6, sizeof v);
+      const uint32_t sv = (uint32_t)v, dv = (uint32_t)(v >> 32);
+      dst[r] = dv;
+      src[m] = sv;
+      const uint32_t mov = sv != dv;
+      m += mov;
+      mask |= mov << (r & 31u);
+    }
+    hdr[2 * b] = mask;
+    hdr[2 * b + 1] = base;
+  }
+  for (uint32_t i = 2 * nb; i < hdr_bytes / 4; ++i) hdr[i] = 0;
+  for (uint32_t i = n; i < dst_bytes / 4; ++i) dst[i] = 0;
+  const uint32_t src_bytes = round16(4u * m);
+  for (uint32_t i = m; i < src_bytes / 4; ++i) src[i] = 0;
+  return hdr_bytes + dst_bytes + src_bytes;
+}
+#undef MVZ_GATHER8
+#endif
+
+}  // namespace
+
+uint64_t mvz_bound(uint64_t n_recs, uint64_t n_frames) {
+  const uint64_t tiles = n_recs / kMvzTileRecs + n_frames;  // >= Σ ceil(n_i / kMvzTileRecs)
+  // per tile: header, the padding of its three sections, the slack of the 64-byte compress stores
+  return tiles * (uint64_t)(round16(8u * (kMvzTileRecs / 32u)) + 48u + 64u) + 8u * n_recs + 64u;
+}
+
+uint64_t mvz_encode_frame(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t* tile_end16) {
+  uint64_t at = 0;
+  uint32_t t = 0;
+  for (uint32_t r = 0; r < n; r += kMvzTileRecs, ++t) {
+    const uint32_t nt = n - r < kMvzTileRecs ? n - r : kMvzTileRecs;
+    uint32_t bytes;
+#if defined(__x86_64__)
+    if (have_vbmi() && nt >= 32) bytes = mvz_tile_vbmi(in + (size_t)kRec * r, nt, out + at);
+    else
+#endif
+      bytes = mvz_tile_scalar(in + (size_t)kRec * r, nt, out + at);
+    at += bytes;
+    tile_end16[t] = (uint32_t)(at >> 4);
+  }
+  return at;
+}
+
+// staging copy of an encoded piece: full aligned lines with streaming stores (the buffer is read next by the DMA engine)
+void stream_copy(const uint8_t* from, uint8_t* to, uint64_t bytes) {
+#if defined(__x86_64__)
+  if (!plain_stores() && ((reinterpret_cast<uintptr_t>(to) | reinterpret_cast<uintptr_t>(from)) & 15u) == 0) {
+    uint64_t i = 0;
+    for (; i + 16 <= bytes; i += 16)
+      _mm_stream_si128(reinterpret_cast<__m128i*>(to + i), _mm_load_si128(reinterpret_cast<const __m128i*>(from + i)));
+    if (i < bytes) memcpy(to + i, from + i, bytes - i);
+    _mm_sfence();
+    return;
+  }
+#endif
+  memcpy(to, from, bytes);
 }
 
 }  // namespace mscan

@@ -51,6 +51,7 @@ struct __align__(16) TileDesc {
 struct FrameMeta {
   uint64_t o0, o1;
   DevGeom g;
+  uint32_t tile0;  // mvz: index of the frame's first tile in the tile directory
 };
 
 __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
@@ -58,7 +59,9 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
   m.o0 = 0;
   m.o1 = 0;
   m.g = DevGeom{0, 0, 0, 0};
+  m.tile0 = 0;
   if (f < a.n_frames) {
+    if (a.frame_tile0) m.tile0 = __ldg(a.frame_tile0 + f);
     m.o0 = __ldg(a.rec_off + f);
     m.o1 = __ldg(a.rec_off + f + 1);
     const uint32_t gi = a.frame_geom ? __ldg(a.frame_geom + f) : 0u;
@@ -79,9 +82,16 @@ __device__ __forceinline__ FrameMeta load_meta(const ScanArgs& a, uint32_t f) {
 // dst_x, dst_y — mscan_mv8) instead of the native 40-byte layout. Same ring, same stage size; a stage then
 // carries 2560 records, and since an 8-byte record never straddles a 16-byte boundary the tiles are cut
 // on the aligned byte stream rather than on record counts.
-template <bool kGlobalCnt, int kConsWarps, bool kCnt16, bool kPacked>
+// kLayout: kLayoutNative / kLayoutMv8 / kLayoutMvz. mvz (host_project.cpp): the projected records with static
+// macroblocks elided — a tile is {mask, base} per block of 32 records, one u32 dst per record, one u32 src per MOVING
+// record. A block without a moving record costs one broadcast load and a branch; everything that survives is rebuilt to
+// the exact (src, dst) pair and goes through the same int32 test.
+template <bool kGlobalCnt, int kConsWarps, bool kCnt16, int kLayout>
 __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1) ka_scan_kernel(const __grid_constant__ ScanArgs a) {
   static_assert(!(kGlobalCnt && kCnt16), "global counters are always 32-bit");
+  constexpr bool kPacked = kLayout != (int)kLayoutNative;  // 8-byte-or-less records: half-size stages, sleeping waits
+  constexpr bool kMv8 = kLayout == (int)kLayoutMv8;
+  constexpr bool kMvz = kLayout == (int)kLayoutMvz;
   constexpr uint32_t kStride = kPacked ? kPackedBytes : kRecBytes;
   constexpr uint32_t kTile = kPacked ? kTileBytesPacked : kTileBytes;  // bytes per ring stage
   constexpr int kCons = kConsWarps * 32;
@@ -136,16 +146,48 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           a.counts[f_cur] = 0;
         } else {
           const uint32_t n = (uint32_t)n64;
+          if (kMvz) {
+            const uint32_t n_tiles = (n + kMvzTileRecs - 1) / kMvzTileRecs;
+            const uint32_t* dir = a.tile_dir + m_cur.tile0;
+            uint32_t e0 = __ldg(dir), e1 = __ldg(dir + 1);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+              const uint32_t e2 = (t + 2 <= n_tiles) ? __ldg(dir + t + 2) : 0u;  // next tile's end, loaded a trip ahead
+              const uint32_t bytes = (e1 - e0) << 4;
+              mbar_wait<kPacked>(bar_empty0 + 8 * stage, phase ^ 1u);
+              TileDesc td;
+              td.n_rec = min(kMvzTileRecs, n - t * kMvzTileRecs);
+              td.byte_off = 0;
+              td.frame = f_cur;
+              td.last = (t + 1 == n_tiles) ? 1u : 0u;
+              td.gw = m_cur.g.gw;
+              td.gh = m_cur.g.gh;
+              td.y_min = m_cur.g.y_min;
+              td.y_max = m_cur.g.y_max;
+              desc[stage] = td;
+              mbar_arrive_expect_tx(bar_full0 + 8 * stage, bytes);
+              bulk_g2s(smem_u32(ring + (size_t)stage * kTile), a.recs + ((size_t)e0 << 4), bytes, bar_full0 + 8 * stage, policy);
+              if (++stage == stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              e0 = e1;
+              e1 = e2;
+            }
+            f_cur = f_next;
+            m_cur = m_next;
+            f_next = f_next2;
+            continue;
+          }
           const uint64_t byte0 = m_cur.o0 * (uint64_t)kStride;
           const uint32_t d = (uint32_t)(byte0 & 15u);
           const unsigned char* src = a.recs + (byte0 - d);
           // native: tile t holds records [512t, 512t+512); packed: tile t holds the records that lie in
           // bytes [20480t, 20480t+20480) of the 16-byte aligned stream starting at src
-          const uint32_t n_tiles = kPacked ? (uint32_t)((d + (uint64_t)kPackedBytes * n + kTile - 1) / kTile)
+          const uint32_t n_tiles = kMv8 ? (uint32_t)((d + (uint64_t)kPackedBytes * n + kTile - 1) / kTile)
                                            : (n + kTileRec - 1) / kTileRec;
           for (uint32_t t = 0; t < n_tiles; ++t) {
             uint32_t nr, bytes, boff;
-            if (kPacked) {
+            if (kMv8) {
               const uint32_t r_lo = t ? (uint32_t)(((uint64_t)t * kTile - d) / kPackedBytes) : 0u;
               const uint32_t r_hi = (uint32_t)min((uint64_t)n, ((uint64_t)(t + 1) * kTile - d) / kPackedBytes);
               nr = r_hi - r_lo;
@@ -225,7 +267,41 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
         *gy_out = gy;
         return (mag >= ithr && in) ? gy * gw + gx : -1;                                              // :251
       };
-      if (kPacked) {
+      // run-length merge of equal neighbouring keys inside the warp (one record per lane), then the votes
+      auto merge_vote = [&](int32_t key, int32_t gy) {
+        const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (key != prev);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        if (head && key >= 0) {
+          const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
+          const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
+          vote(key, gy, next - lane);
+          voted = true;
+        }
+      };
+      if (kMvz) {
+        const unsigned char* sb = ring + (size_t)stage * kTile;
+        const uint32_t n_rec = td.n_rec, nb = (n_rec + 31u) >> 5;
+        const uint32_t hdr_bytes = (8u * nb + 15u) & ~15u, dst_bytes = (4u * n_rec + 15u) & ~15u;
+        const uint2* hdr = reinterpret_cast<const uint2*>(sb);
+        const uint32_t* dstA = reinterpret_cast<const uint32_t*>(sb + hdr_bytes);
+        const uint32_t* srcA = reinterpret_cast<const uint32_t*>(sb + hdr_bytes + dst_bytes);
+        const bool skip_static = ithr > 0;  // a record with src == dst has mag_sq == 0: it cannot vote while T² > 0
+        for (uint32_t b = cwarp; keep_any && b < nb; b += kConsWarps) {
+          const uint2 h = hdr[b];  // {mask of moving records, index of the block's first src}
+          if (skip_static && h.x == 0) continue;
+          const uint32_t r = b * 32 + lane;
+          const bool moving = (h.x >> lane) & 1u;
+          int32_t key = -1, gy = 0;
+          if (r < n_rec && (moving || !skip_static)) {
+            const uint32_t d = dstA[r];
+            const uint32_t sv = moving ? srcA[h.y + (uint32_t)__popc(h.x & ((1u << lane) - 1u))] : d;
+            key = key_of((int32_t)(int16_t)(sv & 0xFFFFu), (int32_t)sv >> 16, (int32_t)(int16_t)(d & 0xFFFFu), (int32_t)d >> 16, &gy);
+          }
+          if (!__any_sync(0xffffffffu, key >= 0)) continue;
+          merge_vote(key, gy);
+        }
+      } else if (kMv8) {
         // Projected records, two per lane: one LDS.128 per 16-byte slot of the stage. A record whose src equals its dst
         // (w.x == w.y: a static macroblock — about 90 % of a CCTV stream) has mag_sq == 0 and cannot vote while the
         // threshold is positive, so one compare per record decides, and a warp trip without a moving record costs the
@@ -297,16 +373,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           }
           // nothing to vote in this warp trip (static macroblocks: the common CCTV case) — skip the merge
           if (!__any_sync(0xffffffffu, key >= 0)) continue;
-          // run-length merge of equal neighbouring keys inside the warp
-          const int32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
-          const bool head = (lane == 0) || (key != prev);
-          const uint32_t heads = __ballot_sync(0xffffffffu, head);
-          if (head && key >= 0) {
-            const uint32_t above = (lane == 31) ? 0u : (heads & (0xFFFFFFFEu << lane));
-            const uint32_t next = above ? (uint32_t)(__ffs(above) - 1) : 32u;
-            vote(key, gy, next - lane);
-            voted = true;
-          }
+          merge_vote(key, gy);
         }
       }
       __syncwarp();
@@ -549,7 +616,7 @@ bool scan_plan_for(const DevGeom* geoms, uint32_t n_geoms, uint32_t smem_optin, 
 }
 
 namespace {
-template <bool kPacked>
+template <int kPacked>
 cudaError_t configure_all(int v) {
   const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
   cudaError_t e = cudaFuncSetAttribute(ka_scan_kernel<false, 8, false, kPacked>, attr, v);
@@ -561,7 +628,7 @@ cudaError_t configure_all(int v) {
   return e;
 }
 
-template <bool kPacked>
+template <int kPacked>
 void launch_one(const ScanArgs& a, const ScanPlan& plan, uint32_t grid, cudaStream_t st) {
   const bool wide = plan.cons_warps == 16;
   const uint32_t threads = plan.cons_warps * 32 + 32;
@@ -579,8 +646,9 @@ void launch_one(const ScanArgs& a, const ScanPlan& plan, uint32_t grid, cudaStre
 }  // namespace
 
 cudaError_t scan_configure(uint32_t smem_optin) {
-  cudaError_t e = configure_all<false>((int)smem_optin);
-  if (e == cudaSuccess) e = configure_all<true>((int)smem_optin);
+  cudaError_t e = configure_all<(int)kLayoutNative>((int)smem_optin);
+  if (e == cudaSuccess) e = configure_all<(int)kLayoutMv8>((int)smem_optin);
+  if (e == cudaSuccess) e = configure_all<(int)kLayoutMvz>((int)smem_optin);
   if (e == cudaSuccess) e = scan_cluster_configure(smem_optin);
   return e;
 }
@@ -594,8 +662,9 @@ cudaError_t scan_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cu
   if (a.n_frames == 0) return cudaSuccess;
   if (plan.cluster) return scan_cluster_launch(a, plan, num_sms, st);
   const uint32_t grid = scan_grid(plan, num_sms, a.n_frames);
-  if (a.packed) launch_one<true>(a, plan, grid, st);
-  else launch_one<false>(a, plan, grid, st);
+  if (a.packed == kLayoutMvz) launch_one<(int)kLayoutMvz>(a, plan, grid, st);
+  else if (a.packed == kLayoutMv8) launch_one<(int)kLayoutMv8>(a, plan, grid, st);
+  else launch_one<(int)kLayoutNative>(a, plan, grid, st);
   return cudaGetLastError();
 }
 

@@ -349,6 +349,7 @@ cudaError_t scan_cluster_configure(uint32_t smem_optin) {
 cudaError_t scan_cluster_launch(const ScanArgs& a, const ScanPlan& plan, int num_sms, cudaStream_t st) {
   if (a.n_frames == 0) return cudaSuccess;
   if (std::getenv("MSCAN_KA_FAIL_CLUSTER_LAUNCH")) return cudaErrorLaunchOutOfResources;  // exercises the caller's fallback
+  if (a.packed == kLayoutMvz) return cudaErrorInvalidValue;  // the cluster kernel reads native and mv8 records only
   const uint32_t C = plan.cluster;
   uint32_t clusters = (uint32_t)num_sms / C;
   if (clusters > a.n_frames) clusters = a.n_frames;

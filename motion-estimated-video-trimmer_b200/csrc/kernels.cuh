@@ -36,9 +36,14 @@ struct ScanArgs {
   uint32_t max_cells;          // vote counters per CTA (shared memory, or a slice of cnt_scratch)
   uint32_t max_bit_words;      // words per bit-row buffer
   uint32_t adj8;               // extension: 8-neighbour clusters (reference is 4-neighbour only)
-  uint32_t packed;             // records are mscan_mv8 projections, not native AVMotionVector
+  uint32_t packed;             // record layout: 0 native AVMotionVector, 1 mscan_mv8 projections, 2 mvz (host_project.cpp)
   uint32_t* cnt_scratch;       // zeroed global scratch, grid × max_cells, only when plan.global_cnt
+  // mvz only: recs = base of the segment's tiles; tile_dir[k] = start of tile k in 16-byte units from recs (tile k ends
+  // at tile_dir[k + 1]); frame_tile0[f] = index of frame f's first tile. rec_off still gives the record counts.
+  const uint32_t* tile_dir;
+  const uint32_t* frame_tile0;
 };
+constexpr uint32_t kLayoutNative = 0, kLayoutMv8 = 1, kLayoutMvz = 2;
 
 struct ScanPlan {
   uint32_t stages;
@@ -93,6 +98,13 @@ cudaError_t segments_launch(const SegArgs& a, uint32_t n_videos, cudaStream_t st
 
 // ---- host side: projection of native records to mscan_mv8 (host_project.cpp; plain C++ with AVX-512 paths)
 void project_records(const uint8_t* in, uint64_t n, uint64_t* out);
+// mvz: projected records with static macroblocks elided (format: host_project.cpp). kMvzTileRecs records per tile.
+constexpr uint32_t kMvzTileRecs = 1024;
+uint64_t mvz_bound(uint64_t n_recs, uint64_t n_frames);  // bytes the encoding of n_recs records in n_frames frames can take, incl. slack
+// encodes ONE frame of n native records at `out` (16-byte aligned); tile_end16[t] = end of tile t in 16-byte units
+// from `out`; returns the bytes written (a multiple of 16)
+uint64_t mvz_encode_frame(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t* tile_end16);
+void stream_copy(const uint8_t* from, uint8_t* to, uint64_t bytes);
 
 // ---- aux: exclusive scan of per-frame record counts, synthetic stream generation
 cudaError_t offsets_launch(const uint32_t* counts, uint32_t n, uint64_t* off, uint64_t* block_scratch,

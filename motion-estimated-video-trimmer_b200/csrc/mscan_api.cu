@@ -91,7 +91,12 @@ struct Slab {
   uint32_t frames = 0;  // frames staged since the slab was recycled
   // The open segment = frames [seg_frame0, frames): one record format, one K-A launch. A slab carries any
   // number of segments (chunk workers may feed different formats); they are launched in order on `stream`.
-  bool packed = false;        // the open segment holds mscan_mv8 projections (8 B), not native records (40 B)
+  uint8_t fmt = 0;            // record layout of the open segment: kLayoutNative (40 B), kLayoutMv8 (8 B) or kLayoutMvz
+  // mvz segments: tile directory (start of every tile in 16-byte units from the segment base, + the end of the last)
+  // and each frame's first tile; a segment of k tiles uses k + 1 directory slots
+  uint32_t *d_tile_dir = nullptr, *h_tile_dir = nullptr, *d_frame_tile0 = nullptr, *h_frame_tile0 = nullptr;
+  uint32_t dir_slots = 0;     // directory slots used since the slab was recycled
+  uint32_t seg_dir0 = 0;      // first directory slot of the open segment
   uint32_t seg_frame0 = 0;
   uint32_t seg_slot0 = 0;     // first rec_off slot of the open segment (a segment of k frames uses k+1 slots)
   uint64_t seg_byte0 = 0;     // 256-byte aligned offset of the open segment's first record
@@ -331,6 +336,7 @@ struct mscan_ctx {
   // slabs
   uint64_t slab_bytes = 0;
   uint32_t slab_frames = 0;
+  uint32_t slab_dir_cap = 0;  // tile-directory slots per slab
   Slab slabs[kSlabs];
   int cur = 0;
 
@@ -371,7 +377,7 @@ struct mscan_ctx {
   int pack_threads = 0;  // threads of the shared pool one large submit of this context may use; 0 → all
   uint32_t win_shift = 21;  // log2 of the H2D copy window (2 MiB: 38 µs on a Gen5 x16 link against ~3 µs to enqueue a copy)
   // counters written outside `mu` (folded into `stats` by mscan_get_stats)
-  std::atomic<uint64_t> a_h2d_bytes{0}, a_records_projected{0}, a_project_ns{0};
+  std::atomic<uint64_t> a_h2d_bytes{0}, a_records_projected{0}, a_project_ns{0}, a_records_elided{0}, a_elided_bytes{0};
 
   // MSCAN_TRACE=1: wall time per ABI entry point (including time spent waiting for the context mutex),
   // printed to stderr by mscan_destroy — the role of the reference's TIMER_START/END + TimingCollector
@@ -428,6 +434,8 @@ void fold_stats(mscan_ctx* c) {
   c->stats.h2d_bytes += c->a_h2d_bytes.exchange(0, std::memory_order_relaxed);
   c->stats.records_projected += c->a_records_projected.exchange(0, std::memory_order_relaxed);
   c->stats.project_ms += (double)c->a_project_ns.exchange(0, std::memory_order_relaxed) * 1e-6;
+  c->stats.records_elided += c->a_records_elided.exchange(0, std::memory_order_relaxed);
+  c->stats.elided_bytes += c->a_elided_bytes.exchange(0, std::memory_order_relaxed);
 }
 
 // No exception crosses the ABI: every entry point that can allocate is a function-try-block ending here.
@@ -673,14 +681,22 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   CU(cudaEventRecord(s.copied, s.stream));  // every H2D copy of the slab so far precedes this point
   ScanArgs a = base_args(c);
   a.recs = s.d_recs + s.seg_byte0;
-  a.packed = s.packed ? 1u : 0u;
+  a.packed = s.fmt;
+  if (s.fmt == kLayoutMvz) {
+    const uint32_t n_dir = s.dir_slots - s.seg_dir0;  // tiles + 1
+    CU(cudaMemcpyAsync(s.d_tile_dir + s.seg_dir0, s.h_tile_dir + s.seg_dir0, sizeof(uint32_t) * n_dir, cudaMemcpyHostToDevice, s.stream));
+    CU(cudaMemcpyAsync(s.d_frame_tile0 + s.seg_frame0, s.h_frame_tile0 + s.seg_frame0, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s.stream));
+    c->a_h2d_bytes.fetch_add(sizeof(uint32_t) * ((uint64_t)n_dir + n), std::memory_order_relaxed);
+    a.tile_dir = s.d_tile_dir + s.seg_dir0;
+    a.frame_tile0 = s.d_frame_tile0 + s.seg_frame0;
+  }
   a.rec_off = s.d_rec_off + s.seg_slot0;
   a.frame_geom = s.d_geom + s.seg_frame0;
   a.geoms = c->d_geoms;
   a.flags = c->d_flags + s.seg_log_base;
   a.counts = c->d_counts + s.seg_log_base;
   a.n_frames = n;
-  const ScanPlan& plan = s.packed ? c->plan_packed : c->plan;
+  const ScanPlan& plan = s.fmt != kLayoutNative ? c->plan_packed : c->plan;
   a.stages = plan.stages;
   a.max_cells = plan.cells;
   a.max_bit_words = plan.bit_words;
@@ -694,6 +710,7 @@ int launch_segment(mscan_ctx* c, Slab& s) {
   s.bytes = (s.bytes + 255) & ~255ull;
   s.seg_byte0 = s.bytes;
   s.seg_recs = 0;
+  s.seg_dir0 = s.dir_slots;
   s.staged = false;
   s.reserved_end.store(s.bytes, std::memory_order_release);
   s.copy_head = s.bytes;
@@ -708,6 +725,8 @@ void recycle_slab(mscan_ctx* c, Slab& s) {
   s.seg_slot0 = 0;
   s.seg_byte0 = 0;
   s.seg_recs = 0;
+  s.dir_slots = 0;
+  s.seg_dir0 = 0;
   s.staged = false;
   s.copy_head = 0;
   s.reserved_end.store(0, std::memory_order_release);
@@ -1040,6 +1059,8 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   c->log_limit = c->log_cap;
   c->slab_bytes = slab_bytes ? ((slab_bytes + 255) & ~255ull) : (64ull << 20);
   c->slab_frames = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(c->slab_bytes / 1024, 4096), 1u << 22);
+  // every frame with records has at least one tile and a tile is at most ~8.4 KB; + one closing slot per segment
+  c->slab_dir_cap = (uint32_t)std::min<uint64_t>(2ull * c->slab_frames + c->slab_bytes / 2048 + 16, 1u << 24);
   if (const char* w = std::getenv("MSCAN_COPY_WINDOW_KB")) {  // experiments: H2D copy window, rounded down to a power of two
     const long kb = std::atol(w);
     uint32_t sh = 16;
@@ -1090,6 +1111,10 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
     CUB_(cudaHostAlloc((void**)&s.h_rec_off, sizeof(uint64_t) * (2 * (size_t)c->slab_frames + 2), cudaHostAllocDefault));
     CUB_(cudaHostAlloc((void**)&s.h_geom, sizeof(uint32_t) * c->slab_frames, cudaHostAllocDefault));
     CUB_(cudaHostAlloc((void**)&s.h_pts, sizeof(double) * c->slab_frames, cudaHostAllocDefault));
+    CUB_(cudaMalloc((void**)&s.d_tile_dir, sizeof(uint32_t) * c->slab_dir_cap));
+    CUB_(cudaMalloc((void**)&s.d_frame_tile0, sizeof(uint32_t) * c->slab_frames));
+    CUB_(cudaHostAlloc((void**)&s.h_tile_dir, sizeof(uint32_t) * c->slab_dir_cap, cudaHostAllocDefault));
+    CUB_(cudaHostAlloc((void**)&s.h_frame_tile0, sizeof(uint32_t) * c->slab_frames, cudaHostAllocDefault));
   }
 #undef CUB_
   *out = c;
@@ -1127,6 +1152,10 @@ int mscan_destroy(mscan_ctx* c) {
     if (s.d_geom) cudaFree(s.d_geom);
     if (s.h_geom) cudaFreeHost(s.h_geom);
     if (s.h_pts) cudaFreeHost(s.h_pts);
+    if (s.d_tile_dir) cudaFree(s.d_tile_dir);
+    if (s.d_frame_tile0) cudaFree(s.d_frame_tile0);
+    if (s.h_tile_dir) cudaFreeHost(s.h_tile_dir);
+    if (s.h_frame_tile0) cudaFreeHost(s.h_frame_tile0);
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -1250,6 +1279,22 @@ int mscan_video_open(mscan_ctx* c, uint32_t video_id, int width, int height) {
 // How one reservation gets its records into the slab (decided under mu, executed outside it).
 enum FillKind { kFillNone = 0, kFillProject, kFillMemcpy, kFillInPlace };
 
+// Commits a reservation whose bytes are in place: the copy windows first (staged reservations), then the segment's
+// writer count (launch_segment waits for the latter).
+static void commit_fill(mscan_ctx* c, Slab& s, bool staged, uint64_t off, uint64_t nbytes) {
+  bool completed_window = false;
+  if (staged) {
+    std::atomic_thread_fence(std::memory_order_release);
+    for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
+      if (s.pend[k].fetch_sub(1, std::memory_order_acq_rel) == 1) completed_window = true;
+  }
+  const uint64_t end_res = s.reserved_end.load(std::memory_order_acquire);
+  s.writers.fetch_sub(1, std::memory_order_release);
+  // after the decrement `s` may be launched and recycled by another thread at any moment; pumping is state-based
+  // and therefore still safe (it then finds nothing, or windows of the slab's next life)
+  if (completed_window && (end_res >> c->win_shift) > (off >> c->win_shift)) try_pump(c, s);
+}
+
 // Executes one reservation's fill outside the context mutex, then commits it.
 static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, uint64_t nbytes, const uint8_t* from,
                            uint64_t n_recs) {
@@ -1272,19 +1317,177 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
     if (e != cudaSuccess) rc = MSCAN_ERR_CUDA;
     c->a_h2d_bytes.fetch_add(nbytes, std::memory_order_relaxed);
   }
-  // commit: the windows first, then the segment's writer count (launch_segment waits for the latter)
-  bool completed_window = false;
-  if (kind == kFillProject || kind == kFillMemcpy) {
-    std::atomic_thread_fence(std::memory_order_release);
-    for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
-      if (s.pend[k].fetch_sub(1, std::memory_order_acq_rel) == 1) completed_window = true;
-  }
-  const uint64_t end_res = s.reserved_end.load(std::memory_order_acquire);
-  s.writers.fetch_sub(1, std::memory_order_release);
-  // after the decrement `s` may be launched and recycled by another thread at any moment; pumping is state-based
-  // and therefore still safe (it then finds nothing, or windows of the slab's next life)
-  if (completed_window && (end_res >> c->win_shift) > (off >> c->win_shift)) try_pump(c, s);
+  commit_fill(c, s, kind == kFillProject || kind == kFillMemcpy, off, nbytes);
   return rc;
+}
+
+// mscan_submit under MSCAN_STAGING_ELIDE: the calling thread encodes its native records as mvz (host_project.cpp:
+// static macroblocks shrink to 4 bytes + a mask bit) into a private scratch, then reserves exactly the encoded size,
+// copies it into the pinned ring outside the mutex and commits. The caller (submit_impl) has reserved the video-local
+// indices [vbase, vbase + n_frames) and released the mutex.
+static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                        const uint8_t* src, uint64_t vbase) {
+  thread_local std::vector<uint8_t> scratch;       // one encoded piece
+  thread_local std::vector<uint32_t> tile_end;     // per tile of the piece: end, 16-byte units from the piece start
+  thread_local std::vector<uint32_t> frame_tile;   // per frame of the piece (+1): index of its first tile
+  thread_local std::vector<uint64_t> frame_end;    // per frame of the piece (+1): end byte offset in the piece
+  std::unique_lock<std::mutex> lk(c->mu, std::defer_lock);
+  uint32_t f = 0;
+  uint64_t src_rec = 0;
+  auto give_back = [&](uint32_t placed) {  // like submit_impl's Rollback
+    if (!lk.owns_lock()) lk.lock();
+    auto it = c->videos.find(video_id);
+    if (it != c->videos.end() && it->second.n_frames == vbase + n_frames) it->second.n_frames = vbase + placed;
+  };
+  while (f < n_frames) {
+    // ---- 1. encode a piece outside the mutex: frames [f, g) with at most kPoolMinRecs records (one frame at least)
+    uint32_t g = f;
+    uint64_t piece_recs = 0;
+    while (g < n_frames && (g == f || piece_recs + rec_count[g] <= kPoolMinRecs)) piece_recs += rec_count[g++];
+    const uint32_t nf = g - f;
+    if (piece_recs && !src) {
+      give_back(f);
+      return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    scratch.resize((size_t)mvz_bound(piece_recs, nf));
+    tile_end.clear();
+    frame_tile.resize((size_t)nf + 1);
+    frame_end.resize((size_t)nf + 1);
+    uint64_t at = 0, done = 0;
+    uint32_t nt = 0;
+    frame_end[0] = 0;
+    for (uint32_t i = 0; i < nf; ++i) {
+      const uint32_t n = rec_count[f + i], tiles = (n + kMvzTileRecs - 1) / kMvzTileRecs;
+      frame_tile[i] = nt;
+      tile_end.resize((size_t)nt + tiles);
+      if (n) {
+        const uint64_t bytes = mvz_encode_frame(src + (size_t)kRecBytes * (src_rec + done), n, scratch.data() + at, tile_end.data() + nt);
+        for (uint32_t t = 0; t < tiles; ++t) tile_end[nt + t] += (uint32_t)(at >> 4);
+        at += bytes;
+      }
+      nt += tiles;
+      done += n;
+      frame_end[(size_t)i + 1] = at;
+    }
+    frame_tile[nf] = nt;
+    c->a_project_ns.fetch_add((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(),
+                              std::memory_order_relaxed);
+    c->a_records_projected.fetch_add(piece_recs, std::memory_order_relaxed);
+    c->a_records_elided.fetch_add(piece_recs, std::memory_order_relaxed);
+    c->a_elided_bytes.fetch_add(at, std::memory_order_relaxed);
+    // ---- 2. place the piece's frames: whole frames, in as many reservations as slab / log / directory room demands
+    uint32_t i = 0;
+    uint64_t rec_i = 0;  // records of the piece's frames [0, i)
+    while (i < nf) {
+      lock_briefly(lk);
+      auto it = c->videos.find(video_id);
+      if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during a submit", video_id);
+      Video& v = it->second;
+      Slab* s = &c->slabs[c->cur];
+      if (s->frames > s->seg_frame0 && (s->fmt != kLayoutMvz || !s->staged)) {
+        int rc = launch_segment(c, *s);
+        if (rc) return give_back(f + i), rc;
+      }
+      if (c->log_head >= c->log_limit) {
+        int rc = launch_segment(c, *s);
+        if (rc) return give_back(f + i), rc;
+        if (!log_find_space(c)) {
+          give_back(f + i);
+          return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos); close videos or create a larger context",
+                      (unsigned long long)c->log_cap);
+        }
+      }
+      const bool opens = s->frames == s->seg_frame0;
+      const uint64_t b0 = frame_end[i], log_room = c->log_limit - c->log_head;
+      uint32_t take = 0;
+      while (i + take < nf && s->frames + take < c->slab_frames && take < log_room) {
+        const uint64_t nb = frame_end[(size_t)i + take + 1] - b0;
+        const uint32_t tiles = frame_tile[(size_t)i + take + 1] - frame_tile[i];
+        if (s->bytes + nb > c->slab_bytes) break;
+        if ((uint64_t)s->dir_slots + (opens ? 1u : 0u) + tiles + 1u > c->slab_dir_cap) break;
+        ++take;
+      }
+      if (take == 0) {
+        if (s->frames == 0) {
+          give_back(f + i);
+          return fail(c, MSCAN_ERR_CAPACITY, "frame with %u records exceeds the slab size (%llu bytes)", rec_count[f + i],
+                      (unsigned long long)c->slab_bytes);
+        }
+        int rc = flush_locked(c);
+        lk.unlock();
+        if (rc) return give_back(f + i), rc;
+        continue;
+      }
+      if (opens) {
+        s->seg_log_base = c->log_head;
+        s->fmt = (uint8_t)kLayoutMvz;
+        s->seg_dir0 = s->dir_slots;
+        s->h_tile_dir[s->dir_slots++] = 0;  // tile 0 of the segment starts at its base
+        std::lock_guard<std::mutex> issue(c->issue_mu);
+        s->staged = true;
+        s->copy_head = s->seg_byte0;
+      }
+      const uint64_t nbytes = frame_end[(size_t)i + take] - b0;
+      if (nbytes && !s->h_recs) {
+        cudaError_t e = use_device(c);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+          give_back(f + i);
+          return fail(c, MSCAN_ERR_NOMEM, "cudaHostAlloc of the staging slab failed: %s", cudaGetErrorString(e));
+        }
+      }
+      const uint64_t off = s->bytes;
+      // piece-relative 16-byte units → segment-relative: frame i's first tile starts where the segment's last one ended
+      const uint32_t rel16 = (uint32_t)((off - s->seg_byte0) >> 4) - (uint32_t)(b0 >> 4);
+      const uint32_t tiles_before = s->dir_slots - s->seg_dir0 - 1;
+      uint64_t r = s->seg_recs, take_recs = 0;
+      const uint32_t slot = s->seg_slot0 + (s->frames - s->seg_frame0);
+      for (uint32_t k = 0; k < take; ++k) {
+        s->h_rec_off[slot + k] = r;
+        r += rec_count[f + i + k];
+        take_recs += rec_count[f + i + k];
+        s->h_geom[s->frames + k] = v.geom;
+        s->h_pts[s->frames + k] = pts[f + i + k];
+        s->h_frame_tile0[s->frames + k] = tiles_before + (frame_tile[(size_t)i + k] - frame_tile[i]);
+      }
+      for (uint32_t t = frame_tile[i]; t < frame_tile[(size_t)i + take]; ++t) s->h_tile_dir[s->dir_slots++] = tile_end[t] + rel16;
+      const uint64_t log_at = c->log_head, vpos = vbase + f + i;
+      if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == log_at && v.extents.back().vpos + v.extents.back().n == vpos)
+        v.extents.back().n += take;
+      else v.extents.push_back(Extent{log_at, take, vpos});
+      v.slab_epoch[c->cur] = s->epoch;
+      c->log_head += take;
+      s->frames += take;
+      s->seg_recs += take_recs;
+      s->bytes += nbytes;
+      const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
+      const uint64_t my_epoch = s->epoch;
+      if (nbytes) {
+        s->writers.fetch_add(1, std::memory_order_relaxed);
+        for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k) s->pend[k].fetch_add(1, std::memory_order_relaxed);
+        s->reserved_end.store(s->bytes, std::memory_order_release);
+      }
+      lk.unlock();
+      if (nbytes) {
+        stream_copy(scratch.data() + b0, s->h_recs + off, nbytes);
+        commit_fill(c, *s, true, off, nbytes);
+      }
+      i += take;
+      rec_i += take_recs;
+      if (slab_full) {
+        lock_briefly(lk);
+        int rc = MSCAN_OK;
+        if (&c->slabs[c->cur] == s && s->epoch == my_epoch) rc = flush_locked(c);
+        lk.unlock();
+        if (rc) return give_back(f + i), rc;
+      }
+    }
+    (void)rec_i;
+    f = g;
+    src_rec += piece_recs;
+  }
+  return MSCAN_OK;
 }
 
 // Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
@@ -1341,11 +1544,18 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   // packed → as is (DMA in place when pinned, memcpy into staging otherwise).
   bool project = false;
   if (!src_packed) {
-    if (c->staging_mode == MSCAN_STAGING_PACK) project = true;
+    if (c->staging_mode == MSCAN_STAGING_PACK || c->staging_mode == MSCAN_STAGING_ELIDE) project = true;
     else if (c->staging_mode == MSCAN_STAGING_NATIVE) project = false;
     else project = !pinned;
   }
-  const bool slab_packed = src_packed || project;
+  // static-elided transport (mvz): native records of a pageable or pinned source, encoded by the calling thread;
+  // the cluster kernel (grids beyond one CTA's shared memory) reads native and mv8 records only
+  if (project && c->staging_mode == MSCAN_STAGING_ELIDE && !c->plan_packed.cluster && !c->plan_packed.global_cnt) {
+    lk.unlock();
+    return submit_elide(c, video_id, n_frames, pts, rec_count, src, vbase);
+  }
+  const uint8_t slab_fmt = (src_packed || project) ? (uint8_t)kLayoutMv8 : (uint8_t)kLayoutNative;
+  const bool slab_packed = slab_fmt != kLayoutNative;
   const bool staged = project || !pinned;
   const FillKind kind = project ? kFillProject : (pinned ? kFillInPlace : kFillMemcpy);
   const uint64_t out_stride = slab_packed ? (uint64_t)kPackedBytes : (uint64_t)kRecBytes;
@@ -1365,7 +1575,7 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during a submit", video_id);
     Video& v = it->second;
     Slab* s = &c->slabs[c->cur];
-    if (s->frames > s->seg_frame0 && (s->packed != slab_packed || s->staged != staged)) {
+    if (s->frames > s->seg_frame0 && (s->fmt != slab_fmt || s->staged != staged)) {
       // one record format and one route (staging / in-place DMA) per segment (= one K-A launch)
       int rc = launch_segment(c, *s);
       if (rc) return rc;
@@ -1401,7 +1611,7 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     if (nbytes && !recs) return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
     if (s->frames == s->seg_frame0) {  // this reservation opens the segment
       s->seg_log_base = c->log_head;
-      s->packed = slab_packed;
+      s->fmt = slab_fmt;
       std::lock_guard<std::mutex> issue(c->issue_mu);
       s->staged = staged;
       s->copy_head = s->seg_byte0;
@@ -1584,9 +1794,21 @@ int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out) {
   return MSCAN_OK;
 }
 
+int mscan_elide_records(const mscan_mv* recs, uint32_t n, void* out, size_t cap, uint32_t* tile_end16, uint32_t tile_cap,
+                        size_t* bytes_out) {
+  if ((n && !recs) || !out || !bytes_out) return MSCAN_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(out) & 15u) return MSCAN_ERR_INVALID;
+  const uint32_t tiles = (n + kMvzTileRecs - 1) / kMvzTileRecs;
+  if (cap < mvz_bound(n, 1) || (tiles && (!tile_end16 || tile_cap < tiles))) return MSCAN_ERR_CAPACITY;
+  *bytes_out = (size_t)mvz_encode_frame(reinterpret_cast<const uint8_t*>(recs), n, static_cast<uint8_t*>(out), tile_end16);
+  return MSCAN_OK;
+}
+
+size_t mscan_elide_bound(uint32_t n) { return (size_t)mvz_bound(n, 1); }
+
 int mscan_set_staging_mode(mscan_ctx* c, int mode) {
   if (!c) return MSCAN_ERR_INVALID;
-  if (mode != MSCAN_STAGING_AUTO && mode != MSCAN_STAGING_PACK && mode != MSCAN_STAGING_NATIVE)
+  if (mode != MSCAN_STAGING_AUTO && mode != MSCAN_STAGING_PACK && mode != MSCAN_STAGING_NATIVE && mode != MSCAN_STAGING_ELIDE)
     return fail(c, MSCAN_ERR_INVALID, "unknown staging mode %d", mode);
   std::lock_guard<std::mutex> lk(c->mu);
   c->staging_mode = mode;

@@ -32,7 +32,7 @@ MV_DTYPE = np.dtype(
 # mscan_mv8: bytes 6..13 of the native record
 MV8_DTYPE = np.dtype([("src_x", "<i2"), ("src_y", "<i2"), ("dst_x", "<i2"), ("dst_y", "<i2")])
 SEG_DTYPE = np.dtype([("start", "<f8"), ("end", "<f8")])
-STAGING_AUTO, STAGING_PACK, STAGING_NATIVE = 0, 1, 2
+STAGING_AUTO, STAGING_PACK, STAGING_NATIVE, STAGING_ELIDE = 0, 1, 2, 3
 
 
 class Params(C.Structure):
@@ -80,6 +80,8 @@ class Stats(C.Structure):
         ("records_projected", C.c_uint64),
         ("project_ms", C.c_double),
         ("peer_bytes", C.c_uint64),
+        ("records_elided", C.c_uint64),
+        ("elided_bytes", C.c_uint64),
     ]
 
 
@@ -146,6 +148,8 @@ SYMBOLS = {
     "mscan_submit_device": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _i, _vp, _P(_u64)]),
     "mscan_device_pci_bus_id": (_i, [_i, C.c_char_p, _i]),
     "mscan_pack_records": (_i, [_vp, _u64, _vp]),
+    "mscan_elide_records": (_i, [_vp, _u32, _vp, C.c_size_t, _vp, _u32, _P(C.c_size_t)]),
+    "mscan_elide_bound": (C.c_size_t, [_u32]),
     "mscan_set_staging_mode": (_i, [_vp, _i]),
     "mscan_set_pack_threads": (_i, [_vp, _i]),
     "mscan_collect_range": (_i, [_vp, _u32, _u64, _u32, _vp, _vp]),
@@ -248,6 +252,54 @@ def pack_records(recs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
     rc = lib().mscan_pack_records(_ptr(recs), len(recs), _ptr(out))
     if rc:
         raise MscanError(rc, "mscan_pack_records")
+    return out
+
+
+def elide_records(recs: np.ndarray):
+    """mscan_elide_records on one frame: (encoded bytes as uint8 array, tile_end16 uint32 array)."""
+    assert recs.dtype == MV_DTYPE and recs.flags["C_CONTIGUOUS"]
+    n = len(recs)
+    cap = lib().mscan_elide_bound(n)
+    raw = np.zeros(cap + 16, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 16
+    out = raw[shift : shift + cap]
+    tiles = (n + 1023) // 1024
+    te = np.zeros(max(tiles, 1), dtype=np.uint32)
+    nbytes = C.c_size_t()
+    rc = lib().mscan_elide_records(_ptr(recs) if n else None, n, out.ctypes.data, cap, _ptr(te), tiles, C.byref(nbytes))
+    if rc:
+        raise MscanError(rc, "mscan_elide_records")
+    return out[: nbytes.value].copy(), te[:tiles].copy()
+
+
+def unelide_records(enc: np.ndarray, tile_end16: np.ndarray, n: int) -> np.ndarray:
+    """Reference decoder of the static-elided form (pure numpy): back to MV8_DTYPE records."""
+    out = np.zeros(n, dtype=MV8_DTYPE)
+    flat = out.view(np.uint32).reshape(n, 2) if n else np.zeros((0, 2), np.uint32)
+    start = 0
+    for t, end16 in enumerate(tile_end16):
+        nt = min(1024, n - 1024 * t)
+        tile = enc[start : int(end16) * 16]
+        nb = (nt + 31) // 32
+        hdr_b, dst_b = (8 * nb + 15) & ~15, (4 * nt + 15) & ~15
+        hdr = tile[:hdr_b].view(np.uint32)[: 2 * nb].reshape(nb, 2)
+        dst = tile[hdr_b : hdr_b + dst_b].view(np.uint32)[:nt]
+        src = tile[hdr_b + dst_b :].view(np.uint32)
+        m = 0
+        for b in range(nb):
+            mask, base = int(hdr[b, 0]), int(hdr[b, 1])
+            assert base == m, "block base must be the running count of moving records"
+            for i in range(min(32, nt - 32 * b)):
+                r = 1024 * t + 32 * b + i
+                flat[r, 1] = dst[32 * b + i]
+                if (mask >> i) & 1:
+                    flat[r, 0] = src[m]
+                    m += 1
+                else:
+                    flat[r, 0] = dst[32 * b + i]
+        assert len(tile) == hdr_b + dst_b + ((4 * m + 15) & ~15)
+        start = int(end16) * 16
+    assert start == len(enc)
     return out
 
 

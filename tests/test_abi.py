@@ -33,7 +33,7 @@ def test_struct_layouts():
     assert C.sizeof(ms.Params) == 56
     assert C.sizeof(ms.Geometry) == 16
     assert C.sizeof(ms.VideoResult) == 40 and ms.RESULT_DTYPE.itemsize == 40
-    assert C.sizeof(ms.Stats) == 96
+    assert C.sizeof(ms.Stats) == 112
     assert ms.MV8_DTYPE.itemsize == 8
     assert C.sizeof(ms.MvgenSpec) == 96  # + scatter, p_rec_move (SURVEY §8(d) config-5 shape)
 
@@ -167,3 +167,27 @@ def test_generator_library_alone_matches_and_spec_stream_shape():
     assert 0.0003 < oob.mean() < 0.003
     # uniform dst: consecutive records are NOT raster-ordered
     assert (np.diff(recs["dst_y"][:1000].astype(int)) < 0).mean() > 0.3
+
+
+def test_elided_form_round_trips_on_cpu():
+    """mscan_elide_records (the wire form of MSCAN_STAGING_ELIDE) against the numpy reference decoder, at tile and
+    block boundaries, for static, mixed and all-moving frames; it never takes more than 8 B/record + per-tile overhead."""
+    from test_oracle_kats import random_frame
+
+    rng = np.random.default_rng(8)
+    cnt, off, recs, pts = ms.synth_host(ms.synth_preset(4, 5), 1, 2)
+    cctv = np.ascontiguousarray(recs[: int(off[1])])
+    moving = random_frame(rng, 3000, 1920, 1080, 5)
+    static = cctv.copy()
+    static["src_x"], static["src_y"] = static["dst_x"], static["dst_y"]
+    for frame in (cctv, moving, static):
+        for n in (0, 1, 31, 32, 33, 1023, 1024, 1025, 2049, len(frame)):
+            if n > len(frame):
+                continue
+            sub = np.ascontiguousarray(frame[:n])
+            enc, te = ms.elide_records(sub)
+            assert len(te) == (n + 1023) // 1024 and len(enc) % 16 == 0
+            assert ms.unelide_records(enc, te, n).tobytes() == ms.pack_records(sub).tobytes()
+            assert len(enc) <= 8 * n + 352 * max(len(te), 1)
+    enc, _ = ms.elide_records(static)
+    assert len(enc) / len(static) < 4.4  # 4 B dst + 8 B header per 32 records

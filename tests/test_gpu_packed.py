@@ -7,6 +7,8 @@ Feed modes (include/motionscan.h, mscan_set_staging_mode / mscan_submit_packed):
   projected-pinned native records in pinned memory, projected anyway (mode PACK)   → K-A<packed>
   packed-pinned    caller-projected mscan_mv8 in pinned memory, DMA'd in place     → K-A<packed>
   packed-pageable  caller-projected mscan_mv8 in pageable memory                   → K-A<packed>
+  elided           native records in pageable memory, sent in the static-elided form (mode ELIDE) → K-A<mvz>
+  elided-pinned    native records in pinned memory, same                           → K-A<mvz>
 """
 import numpy as np
 import pytest
@@ -17,7 +19,7 @@ import oracle_lib as orc
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["native-inplace", "native-staged", "projected", "projected-pinned", "packed-pinned", "packed-pageable"]
+MODES = ["native-inplace", "native-staged", "projected", "projected-pinned", "packed-pinned", "packed-pageable", "elided", "elided-pinned"]
 
 
 def cfg_for(p, w, h):
@@ -30,7 +32,8 @@ class Feeder:
 
     def __init__(self, ctx, mode):
         self.ctx, self.mode, self.pinned = ctx, mode, []
-        ctx.set_staging_mode({"native-staged": ms.STAGING_NATIVE, "projected-pinned": ms.STAGING_PACK}.get(mode, ms.STAGING_AUTO))
+        ctx.set_staging_mode({"native-staged": ms.STAGING_NATIVE, "projected-pinned": ms.STAGING_PACK, "elided": ms.STAGING_ELIDE,
+                              "elided-pinned": ms.STAGING_ELIDE}.get(mode, ms.STAGING_AUTO))
 
     def _pin(self, a):
         h = self.ctx.pinned_array(max(len(a), 1), a.dtype)[: len(a)]
@@ -42,9 +45,9 @@ class Feeder:
         if recs is None:
             recs = np.zeros(0, ms.MV_DTYPE)
         m = self.mode
-        if m in ("native-inplace", "projected-pinned"):
+        if m in ("native-inplace", "projected-pinned", "elided-pinned"):
             return self.ctx.submit(vid, pts, cnt, self._pin(recs))
-        if m in ("native-staged", "projected"):
+        if m in ("native-staged", "projected", "elided"):
             return self.ctx.submit(vid, pts, cnt, recs)
         r8 = ms.pack_records(recs)
         return self.ctx.submit_packed(vid, pts, cnt, self._pin(r8) if m == "packed-pinned" else r8)
@@ -250,3 +253,48 @@ def test_many_tiny_segments_across_the_slab_ring():
     assert np.array_equal(counts, oc) and np.array_equal(flags, of)
     assert segs.tobytes() == osegs.tobytes() and res.decision == ores.decision
     assert st.scan_launches >= 250  # I-frames carry no records and need no launch of their own
+
+
+def test_elided_transport_sends_fewer_bytes_and_counts_them():
+    """MSCAN_STAGING_ELIDE on a CCTV-style clip: identical results, ~4.3 B/record on the wire instead of 8, and the
+    encoder's output decodes (numpy reference decoder) to exactly the projected records."""
+    p = kats.env_params()
+    spec = ms.synth_preset(1, 2)
+    n = 400
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=4)
+    with ms.Context(0, p, 1 << 16, 8 << 20) as ctx:
+        ctx.set_staging_mode(ms.STAGING_ELIDE)
+        ctx.video_open(1, spec.width, spec.height)
+        # per-frame submits (a decode thread's pattern), then one multi-frame submit that spans several pieces and slabs
+        for f in range(100):
+            ctx.submit(1, pts[f : f + 1], cnt[f : f + 1], recs[int(off[f]) : int(off[f + 1])])
+        ctx.submit(1, pts[100:], cnt[100:], recs[int(off[100]) :])
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+    assert np.array_equal(flags, of) and np.array_equal(counts, oc) and of.any()
+    assert st.records_elided == int(off[-1]) == st.records_projected
+    assert 4.0 < st.elided_bytes / st.records_elided < 5.0
+    fr = np.ascontiguousarray(recs[int(off[1]) : int(off[2])])
+    enc, te = ms.elide_records(fr)
+    assert ms.unelide_records(enc, te, len(fr)).tobytes() == ms.pack_records(fr).tobytes()
+
+
+def test_elided_mode_falls_back_to_mv8_for_cluster_sized_grids():
+    """The cluster kernel (8K and larger grids) reads native and mv8 records only: ELIDE then projects to mv8."""
+    from test_oracle_kats import random_frame
+
+    p = kats.env_params(vectors_needed=2)
+    w, h = 7680, 4320
+    rng = np.random.default_rng(12)
+    frames = [random_frame(rng, 20000, w, h, 6) for _ in range(4)]
+    cnt = np.array([len(f) for f in frames], np.uint32)
+    cfg = cfg_for(p, w, h)
+    with ms.Context(0, p) as ctx:
+        ctx.set_staging_mode(ms.STAGING_ELIDE)
+        ctx.video_open(1, w, h)
+        ctx.submit(1, np.arange(4) / 30.0, cnt, kats.cat(*frames))
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+    assert list(counts) == [orc.full_count(cfg, f) for f in frames]
+    assert st.records_elided == 0 and st.records_projected == int(cnt.sum())

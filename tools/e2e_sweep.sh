@@ -22,7 +22,7 @@ PY
 }
 for stores in nt plain; do
   for slab in 2 4 8 16 64; do
-    EXTRA="--slab-mb $slab --e2e-modes producers,packed_pinned" run "stores=$stores slab=${slab}MiB" MSCAN_PROJECT_STORES=$stores
+    EXTRA="--slab-mb $slab --e2e-modes producers,producers_elided,packed_pinned" run "stores=$stores slab=${slab}MiB" MSCAN_PROJECT_STORES=$stores
   done
 done
 for thr in 4 8 12; do
