@@ -607,7 +607,9 @@ def run_gpu(args):
     all_modes = ("producers", "producers_elided", "native_inplace", "projected", "packed_pinned")
     run_modes = [m for m in all_modes if m in args.e2e_modes.split(",")] or list(all_modes)
     for mode in run_modes:
-        ctx.set_staging_mode({"projected": ms.STAGING_PACK, "producers_elided": ms.STAGING_ELIDE}.get(mode, ms.STAGING_AUTO))
+        # producers: mscan_mv8 on the wire (STAGING_PACK); producers_elided: the library's default for a decode thread's
+        # pageable frame (STAGING_AUTO → static-elided form)
+        ctx.set_staging_mode({"projected": ms.STAGING_PACK, "producers": ms.STAGING_PACK}.get(mode, ms.STAGING_AUTO))
         for _ in range(2):
             e2e_out = e2e_step(mode)
         ctx.sync()

@@ -88,7 +88,9 @@ typedef struct mscan_mv8 {
 /* ---- how mscan_submit moves native records to the GPU -------------------- */
 enum {
   MSCAN_STAGING_AUTO = 0,  /* pinned source: DMA the native records in place (no host pass);
-                              pageable source: the staging pass projects to mscan_mv8 (default)  */
+                              pageable source: the staging pass keeps the 8 bytes the path reads — as mscan_mv8,
+                              projected by the worker pool, for submits above 256 Ki records; in the static-elided
+                              form (see MSCAN_STAGING_ELIDE), encoded by the calling thread, below (default)   */
   MSCAN_STAGING_PACK = 1,  /* always project on the host, even from pinned memory                */
   MSCAN_STAGING_NATIVE = 2, /* never project: pageable sources are memcpy'd as 40-byte records   */
   MSCAN_STAGING_ELIDE = 3   /* project, and send static macroblocks (src == dst, ~90 % of a CCTV stream) as their 4 dst

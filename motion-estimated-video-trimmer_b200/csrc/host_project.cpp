@@ -304,13 +304,27 @@ uint64_t mvz_encode_frame(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t*
   return at;
 }
 
-// staging copy of an encoded piece: full aligned lines with streaming stores (the buffer is read next by the DMA engine)
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx512f"))) uint64_t stream_copy_512(const uint8_t* from, uint8_t* to, uint64_t bytes) {
+  uint64_t i = 0;
+  for (; i + 64 <= bytes; i += 64) _mm512_stream_si512(reinterpret_cast<__m512i*>(to + i), _mm512_loadu_si512(from + i));
+  return i;
+}
+}  // namespace
+#endif
+
+// staging copy of an encoded piece (cache-hot scratch → pinned ring): streaming stores, the buffer is read next by the
+// DMA engine, not by this core
 void stream_copy(const uint8_t* from, uint8_t* to, uint64_t bytes) {
 #if defined(__x86_64__)
-  if (!plain_stores() && ((reinterpret_cast<uintptr_t>(to) | reinterpret_cast<uintptr_t>(from)) & 15u) == 0) {
+  if (!plain_stores() && (reinterpret_cast<uintptr_t>(to) & 15u) == 0) {
     uint64_t i = 0;
+    for (; i + 16 <= bytes && ((reinterpret_cast<uintptr_t>(to + i)) & 63u); i += 16)  // up to the first full line
+      _mm_stream_si128(reinterpret_cast<__m128i*>(to + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(from + i)));
+    if (have_vbmi()) i += stream_copy_512(from + i, to + i, bytes - i);
     for (; i + 16 <= bytes; i += 16)
-      _mm_stream_si128(reinterpret_cast<__m128i*>(to + i), _mm_load_si128(reinterpret_cast<const __m128i*>(from + i)));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(to + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(from + i)));
     if (i < bytes) memcpy(to + i, from + i, bytes - i);
     _mm_sfence();
     return;

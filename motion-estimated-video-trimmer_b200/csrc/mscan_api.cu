@@ -1323,10 +1323,14 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
 
 // mscan_submit under MSCAN_STAGING_ELIDE: the calling thread encodes its native records as mvz (host_project.cpp:
 // static macroblocks shrink to 4 bytes + a mask bit) into a private scratch, then reserves exactly the encoded size,
-// copies it into the pinned ring outside the mutex and commits. The caller (submit_impl) has reserved the video-local
-// indices [vbase, vbase + n_frames) and released the mutex.
+// copies it into the pinned ring outside the mutex and commits. The caller (submit_impl) has released the mutex.
 static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                        const uint8_t* src, uint64_t vbase) {
+                        const uint8_t* src, uint64_t* first_frame_out) {
+  // The call's video-local indices [vbase, vbase + n_frames) are reserved in the SAME critical section that places its
+  // first frames: per-frame submits from many decode threads then get video order == log order, and the video stays
+  // one extent instead of one per frame.
+  uint64_t vbase = 0;
+  bool have_vbase = false;
   thread_local std::vector<uint8_t> scratch;       // one encoded piece
   thread_local std::vector<uint32_t> tile_end;     // per tile of the piece: end, 16-byte units from the piece start
   thread_local std::vector<uint32_t> frame_tile;   // per frame of the piece (+1): index of its first tile
@@ -1335,6 +1339,7 @@ static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
   uint32_t f = 0;
   uint64_t src_rec = 0;
   auto give_back = [&](uint32_t placed) {  // like submit_impl's Rollback
+    if (!have_vbase) return;
     if (!lk.owns_lock()) lk.lock();
     auto it = c->videos.find(video_id);
     if (it != c->videos.end() && it->second.n_frames == vbase + n_frames) it->second.n_frames = vbase + placed;
@@ -1384,6 +1389,12 @@ static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
       auto it = c->videos.find(video_id);
       if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during a submit", video_id);
       Video& v = it->second;
+      if (!have_vbase) {
+        vbase = v.n_frames;
+        v.n_frames += n_frames;
+        have_vbase = true;
+        if (first_frame_out) *first_frame_out = vbase;
+      }
       Slab* s = &c->slabs[c->cur];
       if (s->frames > s->seg_frame0 && (s->fmt != kLayoutMvz || !s->staged)) {
         int rc = launch_segment(c, *s);
@@ -1521,6 +1532,15 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   lock_briefly(lk);
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+  // static-elided transport (mvz): native records, encoded by the calling thread before it reserves anything; the
+  // cluster kernel (grids beyond one CTA's shared memory) reads native and mv8 records only
+  // (also what AUTO does with a pageable submit small enough that the caller projects alone — a decode thread handing
+  // over its own frame: the encoding costs about what the projection costs and nearly halves the bytes on the link)
+  const bool elide = c->staging_mode == MSCAN_STAGING_ELIDE || (c->staging_mode == MSCAN_STAGING_AUTO && !pinned && total <= kPoolMinRecs);
+  if (!src_packed && elide && !c->plan_packed.cluster && !c->plan_packed.global_cnt) {
+    lk.unlock();
+    return submit_elide(c, video_id, n_frames, pts, rec_count, src, first_frame_out);
+  }
   const uint64_t vbase = it->second.n_frames;  // this call owns video-local indices [vbase, vbase + n_frames)
   it->second.n_frames += n_frames;
   if (first_frame_out) *first_frame_out = vbase;
@@ -1547,12 +1567,6 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     if (c->staging_mode == MSCAN_STAGING_PACK || c->staging_mode == MSCAN_STAGING_ELIDE) project = true;
     else if (c->staging_mode == MSCAN_STAGING_NATIVE) project = false;
     else project = !pinned;
-  }
-  // static-elided transport (mvz): native records of a pageable or pinned source, encoded by the calling thread;
-  // the cluster kernel (grids beyond one CTA's shared memory) reads native and mv8 records only
-  if (project && c->staging_mode == MSCAN_STAGING_ELIDE && !c->plan_packed.cluster && !c->plan_packed.global_cnt) {
-    lk.unlock();
-    return submit_elide(c, video_id, n_frames, pts, rec_count, src, vbase);
   }
   const uint8_t slab_fmt = (src_packed || project) ? (uint8_t)kLayoutMv8 : (uint8_t)kLayoutNative;
   const bool slab_packed = slab_fmt != kLayoutNative;

@@ -137,6 +137,9 @@ def test_synthetic_clip_every_feed_mode(mode):
     n_rec = int(off[-1])
     if mode.startswith("native"):
         assert st.h2d_bytes >= 40 * n_rec and st.records_projected == 0
+    elif mode.startswith("elided"):
+        assert 4 * n_rec <= st.h2d_bytes < 8 * n_rec  # static records travel as 4 bytes + a mask bit
+        assert st.records_projected == n_rec == st.records_elided
     else:
         assert 8 * n_rec <= st.h2d_bytes < 9 * n_rec  # 8 B/record + per-frame metadata cross PCIe
         assert st.records_projected == (n_rec if mode.startswith("projected") else 0)
