@@ -245,6 +245,10 @@ int mscan_set_staging_mode(mscan_ctx* ctx, int mode);
 /* Threads (including the caller) that project one large submit; 0 → as many as the process may run on
  * (sched_getaffinity), or $MSCAN_PACK_THREADS. Submits below 256 Ki records never leave the calling thread. */
 int mscan_set_pack_threads(mscan_ctx* ctx, int n_threads);
+/* Allocates the pinned staging ring now (3 x slab_bytes) instead of at the first submits of pageable records: a host
+ * whose decode / file threads are about to start calls it right after mscan_create, so the page pinning does not
+ * stall them later. Optional. */
+int mscan_reserve_staging(mscan_ctx* ctx);
 int mscan_flush(mscan_ctx* ctx); /* launch whatever is staged; does not wait */
 /* Per-frame results in submission order. cap = capacity of flags/full_counts (either may be NULL). */
 int mscan_collect(mscan_ctx* ctx, uint32_t video_id, uint8_t* flags, uint32_t* full_counts,

@@ -55,6 +55,7 @@ using namespace mscan;
 namespace {
 
 constexpr int kSlabs = 3;
+constexpr size_t kPendStride = 16;  // copy-window counters sit one per cache line (16 x int32)
 constexpr int kWorkSlots = 16;  // frame queues: one per slab stream (launches on a stream are serialised) + a rotating
                                  // pool for launches on caller streams (mscan_scan_device)
 constexpr uint32_t kMaxGeoms = 4096;
@@ -610,11 +611,14 @@ ScanArgs base_args(mscan_ctx* c) {
 // from every decode thread, a contended std::mutex::lock() puts the loser to sleep in the kernel, and the wake-up costs far
 // more (tens of µs in a VM) than the few hundred ns the holder needs.
 void lock_briefly(std::unique_lock<std::mutex>& lk) {
-  for (int spin = 0; spin < 2000; ++spin) {
-    if (lk.try_lock()) return;
+  for (int round = 0, wait = 1; round < 48; ++round) {  // exponential back-off: 30 threads retrying at full rate would
+    if (lk.try_lock()) return;                          // keep the lock's cache line away from its holder
+    for (int i = 0; i < wait; ++i) {
 #if defined(__x86_64__)
-    _mm_pause();
+      _mm_pause();
 #endif
+    }
+    if (wait < 128) wait *= 2;
   }
   lk.lock();
 }
@@ -637,7 +641,7 @@ int pump_locked(mscan_ctx* c, Slab& s, bool seal) {
   while (s.copy_head < end_res) {
     const uint64_t k = s.copy_head >> c->win_shift, win_end = (k + 1) << c->win_shift;
     if (!seal && end_res < win_end) break;
-    if (s.pend[k].load(std::memory_order_acquire) != 0) break;
+    if (s.pend[k * kPendStride].load(std::memory_order_acquire) != 0) break;
     const uint64_t e = std::min(win_end, end_res);
     CU(cudaMemcpyAsync(s.d_recs + s.copy_head, s.h_recs + s.copy_head, e - s.copy_head, cudaMemcpyHostToDevice, s.stream));
     c->a_h2d_bytes.fetch_add(e - s.copy_head, std::memory_order_relaxed);
@@ -653,8 +657,18 @@ void try_pump(mscan_ctx* c, Slab& s) {
   pump_locked(c, s, false);
 }
 
-void wait_writers(const Slab& s) {
-  for (uint32_t spin = 0; s.writers.load(std::memory_order_acquire) != 0; ++spin) {
+// Every reservation of the open segment has been committed: the in-place ones are counted in `writers`, the staged
+// ones in the copy-window counters of the segment's byte range (no separate count: one contended atomic less per frame).
+bool segment_quiet(const mscan_ctx* c, const Slab& s) {
+  if (s.writers.load(std::memory_order_acquire) != 0) return false;
+  if (s.staged && s.bytes > s.seg_byte0)
+    for (uint64_t k = s.seg_byte0 >> c->win_shift; k <= (s.bytes - 1) >> c->win_shift; ++k)
+      if (s.pend[k * kPendStride].load(std::memory_order_acquire) != 0) return false;
+  return true;
+}
+
+void wait_writers(const mscan_ctx* c, const Slab& s) {
+  for (uint32_t spin = 0; !segment_quiet(c, s); ++spin) {
 #if defined(__x86_64__)
     if (spin < 256) _mm_pause();
     else std::this_thread::yield();
@@ -668,7 +682,7 @@ void wait_writers(const Slab& s) {
 int launch_segment(mscan_ctx* c, Slab& s) {
   const uint32_t n = s.frames - s.seg_frame0;
   if (n == 0) return MSCAN_OK;
-  wait_writers(s);  // fills run outside mu and never need it to commit: this wait is bounded by one frame's projection
+  wait_writers(c, s);  // fills run outside mu and never need it to commit: this wait is bounded by one frame's projection
   std::lock_guard<std::mutex> issue(c->issue_mu);
   CU(use_device(c));
   int rc = pump_locked(c, s, true);
@@ -1099,9 +1113,9 @@ int mscan_create(int device, const mscan_params* p, uint64_t max_log_frames, uin
   CUB_(cudaMalloc((void**)&c->d_counts, sizeof(uint32_t) * c->log_cap));
   for (auto& s : c->slabs) {
     const size_t n_win = (size_t)((c->slab_bytes + 256) >> c->win_shift) + 2;
-    s.pend.reset(new (std::nothrow) std::atomic<int32_t>[n_win]);
+    s.pend.reset(new (std::nothrow) std::atomic<int32_t>[n_win * kPendStride]);
     if (!s.pend) return bail(MSCAN_ERR_NOMEM);
-    for (size_t k = 0; k < n_win; ++k) s.pend[k].store(0, std::memory_order_relaxed);
+    for (size_t k = 0; k < n_win * kPendStride; ++k) s.pend[k].store(0, std::memory_order_relaxed);
     CUB_(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CUB_(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
@@ -1286,13 +1300,11 @@ static void commit_fill(mscan_ctx* c, Slab& s, bool staged, uint64_t off, uint64
   if (staged) {
     std::atomic_thread_fence(std::memory_order_release);
     for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
-      if (s.pend[k].fetch_sub(1, std::memory_order_acq_rel) == 1) completed_window = true;
-  }
-  const uint64_t end_res = s.reserved_end.load(std::memory_order_acquire);
-  s.writers.fetch_sub(1, std::memory_order_release);
-  // after the decrement `s` may be launched and recycled by another thread at any moment; pumping is state-based
+      if (s.pend[k * kPendStride].fetch_sub(1, std::memory_order_acq_rel) == 1) completed_window = true;
+  } else s.writers.fetch_sub(1, std::memory_order_release);
+  // after the last decrement `s` may be launched and recycled by another thread at any moment; pumping is state-based
   // and therefore still safe (it then finds nothing, or windows of the slab's next life)
-  if (completed_window && (end_res >> c->win_shift) > (off >> c->win_shift)) try_pump(c, s);
+  if (completed_window && (s.reserved_end.load(std::memory_order_acquire) >> c->win_shift) > (off >> c->win_shift)) try_pump(c, s);
 }
 
 // Executes one reservation's fill outside the context mutex, then commits it.
@@ -1475,8 +1487,7 @@ static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
       const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
       const uint64_t my_epoch = s->epoch;
       if (nbytes) {
-        s->writers.fetch_add(1, std::memory_order_relaxed);
-        for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k) s->pend[k].fetch_add(1, std::memory_order_relaxed);
+        for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k) s->pend[k * kPendStride].fetch_add(1, std::memory_order_relaxed);
         s->reserved_end.store(s->bytes, std::memory_order_release);
       }
       lk.unlock();
@@ -1659,10 +1670,10 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     f += take;
     const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
     if (nbytes) {
-      s->writers.fetch_add(1, std::memory_order_relaxed);
       if (staged)
         for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k)
-          s->pend[k].fetch_add(1, std::memory_order_relaxed);
+          s->pend[k * kPendStride].fetch_add(1, std::memory_order_relaxed);
+      else s->writers.fetch_add(1, std::memory_order_relaxed);
       s->reserved_end.store(s->bytes, std::memory_order_release);
       // ---- fill + commit outside the mutex -------------------------------------------------------------
       const uint64_t my_epoch = s->epoch;
@@ -1827,6 +1838,21 @@ int mscan_set_staging_mode(mscan_ctx* c, int mode) {
   std::lock_guard<std::mutex> lk(c->mu);
   c->staging_mode = mode;
   return MSCAN_OK;
+}
+
+// Allocates the pinned staging of every slab now instead of at the first staged submit that needs it. Pinning tens of
+// MiB takes the process's address-space lock for ~0.4 ms per MiB: paid lazily it stalls every thread that is faulting in
+// file pages at that moment (8 contexts x 3 slabs x 64 MiB on an 8-GPU box cost a 64-clip batch 0.6 s of its 1.3 s);
+// a host that knows it will feed pageable records calls this right after mscan_create, before its workers start.
+int mscan_reserve_staging(mscan_ctx* c) try {
+  if (!c) return MSCAN_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(c->mu);
+  CU(cudaSetDevice(c->device));
+  for (auto& s : c->slabs)
+    if (!s.h_recs) CU(cudaHostAlloc((void**)&s.h_recs, c->slab_bytes, cudaHostAllocDefault));
+  return MSCAN_OK;
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_set_pack_threads(mscan_ctx* c, int n_threads) try {

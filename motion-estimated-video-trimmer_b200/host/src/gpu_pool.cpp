@@ -2,6 +2,7 @@
 #include "motion_trim/gpu_pool.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 
 #include "motion_trim/config.hpp"
@@ -32,7 +33,11 @@ bool GpuPool::open(int max_gpus) {
   std::vector<std::thread> creators;
   const uint64_t slab_bytes = (uint64_t)std::max(0, Config::slab_mb()) << 20;
   for (int g = 0; g < n; ++g)
-    creators.emplace_back([&, g] { rcs[(size_t)g] = mscan_create(g, &params_, 0, slab_bytes, &made[(size_t)g]); });
+    creators.emplace_back([&, g] {
+      rcs[(size_t)g] = mscan_create(g, &params_, 0, slab_bytes, &made[(size_t)g]);
+      // the pinned staging ring now, not under the feet of the stream threads (see mscan_reserve_staging)
+      if (rcs[(size_t)g] == MSCAN_OK && !std::getenv("MOTION_TRIM_LAZY_STAGING")) mscan_reserve_staging(made[(size_t)g]);
+    });
   for (auto& t : creators) t.join();
   for (int g = 0; g < n; ++g) {
     if (rcs[(size_t)g] != MSCAN_OK) {

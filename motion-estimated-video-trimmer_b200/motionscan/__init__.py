@@ -152,6 +152,7 @@ SYMBOLS = {
     "mscan_elide_bound": (C.c_size_t, [_u32]),
     "mscan_set_staging_mode": (_i, [_vp, _i]),
     "mscan_set_pack_threads": (_i, [_vp, _i]),
+    "mscan_reserve_staging": (_i, [_vp]),
     "mscan_collect_range": (_i, [_vp, _u32, _u64, _u32, _vp, _vp]),
     "mscan_flush": (_i, [_vp]),
     "mscan_collect": (_i, [_vp, _u32, _vp, _vp, _u32, _P(_u32)]),
@@ -392,6 +393,9 @@ class Context:
 
     def set_staging_mode(self, mode: int):
         self._ck(self.L.mscan_set_staging_mode(self.h, mode))
+
+    def reserve_staging(self):
+        self._ck(self.L.mscan_reserve_staging(self.h))
 
     def set_pack_threads(self, n: int):
         self._ck(self.L.mscan_set_pack_threads(self.h, n))

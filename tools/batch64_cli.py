@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--frames", type=int, default=1800)
     ap.add_argument("--dir", default="/dev/shm/mscan_batch64")
     ap.add_argument("--gpus", default="1,2,4,8")
-    ap.add_argument("--streams", type=int, default=2, help="PARALLEL_STREAMS per GPU (shipped env: 2)")
+    ap.add_argument("--streams", default="2", help="PARALLEL_STREAMS per GPU (shipped env: 2; comma list)")
     ap.add_argument("--keep", action="store_true")
     ap.add_argument("--modes", default="default,nopin")
     ap.add_argument("--chunk", default="10", help="CHUNK_DURATION_SEC (comma list: one run per value)")
@@ -56,12 +56,12 @@ def main():
         n_rec += int(off[-1])
     print(f"# generated {args.clips} clips x {args.frames} frames = {n_rec} records ({n_rec * 40 / 1e9:.1f} GB) in {time.time() - t0:.1f} s", flush=True)
     baseline = None
-    combos = [(g, t, c) for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)] for t in args.threads.split(",")
-              for c in args.chunk.split(",")]
-    for g, thr, chunk in combos:
+    combos = [(g, t, c, st) for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)] for t in args.threads.split(",")
+              for c in args.chunk.split(",") for st in args.streams.split(",")]
+    for g, thr, chunk, n_streams in combos:
         env0 = dict(os.environ, MV_THRESHOLD_SQ="4.0", VECTORS_NEEDED="4", CLUSTERS_NEEDED="2", VERTICAL_MASK="0.05", MAX_GAP_SEC="5",
                     PADDING_SEC="0.5", MIN_SAVINGS_PCT="5", CHUNK_DURATION_SEC=chunk, TARGET_FPS="0", THREADS_PER_STREAM=thr,
-                    PARALLEL_STREAMS=str(args.streams))
+                    PARALLEL_STREAMS=n_streams)
         if args.trace:
             env0["MSCAN_TRACE"] = "1"
         # default: the mapped file is pinned and DMA'd in place (40 B/record over PCIe, no host pass); nopin: the chunk
@@ -84,7 +84,7 @@ def main():
             ph = re.search(r"phases \(sum over files, s\): (.*)", r.stdout)
             if args.trace:
                 print("\n".join(ln for ln in r.stderr.splitlines() if "mscan trace" in ln), flush=True)
-            print(json.dumps({"gpus": g, "feed": mode, "threads_per_stream": thr, "chunk_sec": chunk, "phases": ph.group(1) if ph else None, "streams_per_gpu": args.streams, "rc": r.returncode, "files": len(res),
+            print(json.dumps({"gpus": g, "feed": mode, "threads_per_stream": thr, "chunk_sec": chunk, "phases": ph.group(1) if ph else None, "streams_per_gpu": n_streams, "rc": r.returncode, "files": len(res),
                               "batch_wall_s": scan_wall, "process_wall_s": round(wall, 3), "records_per_s": n_rec / scan_wall,
                               "same_results_as_first_run": dec == baseline}), flush=True)
     if not args.keep:

@@ -23,7 +23,9 @@ with ms.Context(0, p, 1 << 20, 64 << 20) as ctx:
     ctx.set_profiling(True)
     for mode, name in ((ms.STAGING_AUTO, "auto"), (ms.STAGING_ELIDE, "elide")):
         ctx.set_staging_mode(mode)
-        for T in (1, 4, 16):
+        for T in [int(x) for x in (sys.argv[1].split(',') if len(sys.argv) > 1 else ['1', '4', '16'])]:
+            if T > len(cpus):
+                continue
             for rep in range(2):
                 ctx.video_open(1, spec.width, spec.height)
                 ctx.reset_stats()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small driver for ncu captures of K-A: builds a device-resident stream and launches ka_scan_kernel a few times.
-    python tools/ka_profile_run.py [records] [native|packed] [preset] [launches]"""
+    python tools/ka_profile_run.py [records] [native|packed] [preset] [launches] [frames]"""
 import sys
 from pathlib import Path
 
@@ -24,6 +24,8 @@ ctx.sync()
 pc = np.zeros(probe, np.uint32)
 ctx.d2h(pc, d)
 n = int(records / pc.mean())
+if len(sys.argv) > 5 and int(sys.argv[5]) > 0:  # exact frame count (bench.py's stream: 100153 frames of preset 4, seed 5)
+    n = int(sys.argv[5])
 d_cnt = ctx.dev_alloc(4 * n)
 d_off = ctx.dev_alloc(8 * (n + 1))
 ctx.synth_counts(spec, 0, n, d_cnt)
