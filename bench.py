@@ -411,6 +411,7 @@ def run_gpu(args):
 
     params = ms.shipped_env_params()
     ctx = ms.Context(local, params, max_log_frames=1 << 20, slab_bytes=args.slab_mb << 20)
+    ctx.reserve_staging()  # the pinned ring now: allocated lazily, a slab's 25 ms would land inside a timed host-fed step
     stream = torch.cuda.Stream()
     sh = stream.cuda_stream
 
