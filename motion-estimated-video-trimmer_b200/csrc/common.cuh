@@ -47,7 +47,7 @@ template <bool kSleep = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   while (!mbar_try_wait(bar, parity)) {
-    if (kSleep) __nanosleep(40);
+    if (kSleep) __nanosleep(40);  // (an exponential back-off to 256 ns was tried: no gain at 1080p, −18 % on the dense 4K field)
   }
 }
 

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
   if (!kGlobalCnt)  // the global scratch is zero on entry and every epilogue leaves it zero
     for (uint32_t i = tid; i < (kCnt16 ? (a.max_cells + 1) / 2 : a.max_cells); i += kThreads) cnt[i] = 0;
   for (uint32_t i = tid; i < a.max_bit_words; i += kThreads) wordv[i] = 0;
+  for (uint32_t i = tid; i < 2 * a.max_bit_words; i += kThreads) bits[i] = 0;
   __syncthreads();
 
   if (warp == 0) {
@@ -395,9 +396,9 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
           // 32-cell words of the FLAT grid (cells [32k, 32k+32)) they fell into; only those are read. A flat word k
           // spans at most two grid rows; its cells are turned into bits of the row-aligned bit-row words with atomicOr
           // after the bit-rows have been cleared.
+          // (the bit-rows of this parity are clean: zeroed at kernel start, and again by the pass-2 warp of the frame
+          // that last used them, which joins this frame's barriers only after it has finished)
           const uint32_t n_bw = (uint32_t)gh * wpr;
-          for (uint32_t i = ctid; i < n_bw; i += kCons) brow[i] = 0;
-          named_bar_sync(kBarCons, kCons);
           const uint32_t n_cells = (uint32_t)gh * (uint32_t)gw;
           const uint32_t n_fw = (n_cells + 31u) >> 5;
           for (uint32_t k0 = cwarp * 32; k0 < n_fw; k0 += kCons) {
@@ -464,6 +465,8 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
               a.counts[td.frame] = total;
               a.flags[td.frame] = (total >= a.clust_need) ? 1 : 0;   // closed form of :288-289
             }
+            __syncwarp();
+            for (uint32_t i = lane; i < n_bw; i += 32) brow[i] = 0;  // leave this parity's bit-rows clean for frame n + 2
           }
         } else if (ctid == 0) {
           a.counts[td.frame] = 0;
