@@ -301,6 +301,9 @@ def run_reference(args):
     if _fixed:
         n_frames = min(n_frames, _fixed)
     cpu, n_rec = cpu_leg(mvgen, params, spec, n_frames, threads, args.steps, args.warmup, repeats=args.ref_repeats)
+    # this arm is the reference's CPU code: nothing of the product may be mapped into it
+    maps = open("/proc/self/maps").read() if os.path.exists("/proc/self/maps") else ""
+    assert "libmotionscan.so" not in maps and "libmscan_feed.so" not in maps, "the reference arm must not load the product library"
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -336,7 +339,8 @@ WORKLOADS = {
     "cctv10min": (1, 2, 18000, "cctv10min: synthetic 10 min 1080p30 CCTV-style clip (BASELINE.json configs[1]) as an MV stream"),
     "dense4k": (2, 3, 3600, "dense4k: synthetic 2 min 4K30 clip with a dense 8x8 MV field, 129 600 records per P-frame "
                 "(BASELINE.json configs[2]) as an MV stream"),
-    "batch64": (3, 100, 64 * 1800, "batch64: 64 synthetic 60 s 1080p30 clips in one batch (BASELINE.json configs[3]) as MV streams"),
+    "batch64": (3, 100, 64 * 1800, "batch64: 64 synthetic 1080p30 clips of 30–120 s (uniform; seeds 100…163) in one batch (BASELINE.json "
+                "configs[3], SURVEY §8(d) config 4) as MV streams"),
 }
 _WORKLOAD_DESC = WORKLOADS["stream1e9"][3]
 
@@ -381,6 +385,46 @@ def build_stream(ctx, ms, spec, frame0, n_frames, sh, stream):
     return d_off, d_recs, d_pts, off, n_rec
 
 
+def batch64_lengths(seed0, n_videos=64, fps=30):
+    """durations uniform in 30–120 s (a fixed pseudo-random function of the video's seed)."""
+    out = []
+    for v in range(n_videos):
+        z = (seed0 + v) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF
+        z ^= z >> 29
+        out.append(30 * fps + int(z % (90 * fps + 1)))
+    return out
+
+
+def build_batch(ctx, ms, preset, seed0, lengths, lo, hi, sh, stream):
+    """Frames [lo, hi) of the concatenation of len(lengths) videos (video v: preset with seed seed0 + v, lengths[v]
+    frames), generated on the device video by video. Returns like build_stream plus the global video start frames."""
+    starts = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    n_frames = hi - lo
+    d_cnt = ctx.dev_alloc(4 * max(n_frames, 1))
+    d_off = ctx.dev_alloc(8 * (n_frames + 1))
+    pieces = []
+    for v, L in enumerate(lengths):
+        a, b = max(lo, int(starts[v])), min(hi, int(starts[v]) + L)
+        if a >= b:
+            continue
+        spec = ms.synth_preset(preset, seed0 + v)
+        spec.frames_per_video = L
+        pieces.append((spec, a - int(starts[v]), b - a, a - lo))
+        ctx.synth_counts(spec, a - int(starts[v]), b - a, d_cnt + 4 * (a - lo), sh)
+    ctx.offsets_from_counts(d_cnt, n_frames, d_off, sh)
+    stream.synchronize()
+    off = np.zeros(n_frames + 1, np.uint64)
+    ctx.d2h(off, d_off)
+    n_rec = int(off[-1])
+    d_recs = ctx.dev_alloc(REC_BYTES * n_rec + 256)
+    d_pts = ctx.dev_alloc(8 * max(n_frames, 1))
+    for spec, f0, n, at in pieces:
+        ctx.synth_fill(spec, f0, n, d_off + 8 * at, d_recs, d_pts + 8 * at, sh)
+    stream.synchronize()
+    ctx.dev_free(d_cnt)
+    return d_off, d_recs, d_pts, off, n_rec, starts
+
+
 def frames_for_records(ctx, spec, records, sh, stream):
     probe = 4096
     d_probe = ctx.dev_alloc(4 * probe)
@@ -420,22 +464,31 @@ def run_gpu(args):
     preset, seed, fixed_frames, _WORKLOAD_DESC = WORKLOADS[args.workload]
     strong = args.scaling == "strong"
     spec = ms.synth_preset(preset, seed if strong else seed + rank)
-    total_frames_all = fixed_frames if fixed_frames is not None else frames_for_records(ctx, spec, args.records, sh, stream)
+    batch_lengths = batch64_lengths(seed if strong else seed + 64 * rank) if args.workload == "batch64" else None
+    if batch_lengths is not None:
+        total_frames_all = int(sum(batch_lengths))
+    else:
+        total_frames_all = fixed_frames if fixed_frames is not None else frames_for_records(ctx, spec, args.records, sh, stream)
     if strong:  # one stream, rank g scans frames [g·F/G, (g+1)·F/G)  
         frame0 = total_frames_all * rank // world
         n_frames = total_frames_all * (rank + 1) // world - frame0
     else:
         frame0, n_frames = 0, total_frames_all
-    d_off, d_recs, d_pts, off, n_rec = build_stream(ctx, ms, spec, frame0, n_frames, sh, stream)
+    fpv = spec.frames_per_video
+    if batch_lengths is not None:  # 64 videos of 30–120 s, seeds 100…163
+        d_off, d_recs, d_pts, off, n_rec, vstarts = build_batch(ctx, ms, preset, seed if strong else seed + 64 * rank, batch_lengths,
+                                                                frame0, frame0 + n_frames, sh, stream)
+    else:
+        d_off, d_recs, d_pts, off, n_rec = build_stream(ctx, ms, spec, frame0, n_frames, sh, stream)
+        vstarts = np.arange(0, frame0 + n_frames + fpv, fpv, dtype=np.int64) if fpv else np.array([0], np.int64)
     d_flags = ctx.dev_alloc(n_frames)
     d_counts = ctx.dev_alloc(4 * n_frames)
     d_segs = ctx.dev_alloc(16 * n_frames)
-    fpv = spec.frames_per_video
 
     def video_offsets(f0, n):
         """Local frame offsets of the videos (pieces of videos at the ends of a strong-scaling share) in [f0, f0+n)."""
-        cuts = sorted({0, n} | {g - f0 for g in range((f0 // fpv + 1) * fpv, f0 + n, fpv)}) if fpv else [0, n]
-        return np.array(cuts, dtype=np.uint64)
+        inner = vstarts[(vstarts > f0) & (vstarts < f0 + n)] - f0
+        return np.array(sorted({0, n} | {int(x) for x in inner}), dtype=np.uint64)
 
     voff = video_offsets(frame0, n_frames)
     n_videos = len(voff) - 1

@@ -32,7 +32,7 @@ BIN = ROOT / "motion-estimated-video-trimmer_b200" / "host" / "motion_trim_b200"
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--clips", type=int, default=64)
-    ap.add_argument("--frames", type=int, default=1800)
+    ap.add_argument("--frames", type=int, default=0, help="frames per clip; 0 = uniform 30–120 s per clip (SURVEY §8(d) config 4)")
     ap.add_argument("--dir", default="/dev/shm/mscan_batch64")
     ap.add_argument("--gpus", default="1,2,4,8")
     ap.add_argument("--streams", default="2", help="PARALLEL_STREAMS per GPU (shipped env: 2; comma list)")
@@ -49,12 +49,18 @@ def main():
     ind, threads = Path(args.dir) / "in", os.cpu_count() or 8
     ind.mkdir(parents=True, exist_ok=True)
     t0, n_rec, expect = time.time(), 0, {}
+    sys.path.insert(0, str(ROOT))
+    from bench import batch64_lengths
+
+    lengths = [args.frames] * args.clips if args.frames else batch64_lengths(100, args.clips)
     for k in range(args.clips):
         spec = ms.synth_preset(3, 100 + k)
-        cnt, off, recs, pts = ms.synth_host(spec, 0, args.frames, n_threads=threads)
-        mvs_io.write_mvs(ind / f"clip{k:03d}.mvs", spec.width, spec.height, int(spec.fps), 1, np.arange(args.frames), cnt, recs)
+        spec.frames_per_video = lengths[k]
+        cnt, off, recs, pts = ms.synth_host(spec, 0, lengths[k], n_threads=threads)
+        mvs_io.write_mvs(ind / f"clip{k:03d}.mvs", spec.width, spec.height, int(spec.fps), 1, np.arange(lengths[k]), cnt, recs)
         n_rec += int(off[-1])
-    print(f"# generated {args.clips} clips x {args.frames} frames = {n_rec} records ({n_rec * 40 / 1e9:.1f} GB) in {time.time() - t0:.1f} s", flush=True)
+    print(f"# generated {args.clips} clips of {min(lengths)}–{max(lengths)} frames ({sum(lengths)} in all) = {n_rec} records "
+          f"({n_rec * 40 / 1e9:.1f} GB) in {time.time() - t0:.1f} s", flush=True)
     baseline = None
     combos = [(g, t, c, st) for g in [int(x) for x in args.gpus.split(",") if int(x) <= max(n_dev.value, 1)] for t in args.threads.split(",")
               for c in args.chunk.split(",") for st in args.streams.split(",")]
