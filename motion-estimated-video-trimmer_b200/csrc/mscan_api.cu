@@ -1874,6 +1874,52 @@ int mscan_flush(mscan_ctx* c) try {
   return on_exception(c);
 }
 
+// Copies pieces of the frame log (flags / counts) to the caller's arrays. A video fed frame by frame by many decode
+// threads next to other videos owns thousands of short extents: instead of two tiny D2H copies per extent (≈ 6 µs each —
+// 74 ms for three interleaved videos of 2 000 frames) the covering range of the log comes over in one copy and is
+// scattered on the host, as long as that range is not much larger than what is asked for.
+namespace {
+struct LogPiece {
+  uint64_t src, n, dst;
+};
+int copy_log_pieces(mscan_ctx* c, const std::vector<LogPiece>& pieces, uint8_t* flags, uint32_t* counts) {
+  if (pieces.empty() || (!flags && !counts)) return MSCAN_OK;
+  uint64_t lo = ~0ull, hi = 0, need = 0;
+  for (const LogPiece& p : pieces) {
+    lo = std::min(lo, p.src);
+    hi = std::max(hi, p.src + p.n);
+    need += p.n;
+  }
+  const uint64_t span = hi - lo;
+  if (pieces.size() > 8 && span <= 4 * need + (1u << 16)) {
+    std::vector<uint8_t> tf;
+    std::vector<uint32_t> tc;
+    if (flags) {
+      tf.resize(span);
+      CU(cudaMemcpyAsync(tf.data(), c->d_flags + lo, span, cudaMemcpyDeviceToHost, c->main_stream));
+    }
+    if (counts) {
+      tc.resize(span);
+      CU(cudaMemcpyAsync(tc.data(), c->d_counts + lo, span * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
+    }
+    CU(cudaStreamSynchronize(c->main_stream));
+    for (const LogPiece& p : pieces) {
+      if (flags) std::memcpy(flags + p.dst, tf.data() + (p.src - lo), p.n);
+      if (counts) std::memcpy(counts + p.dst, tc.data() + (p.src - lo), p.n * sizeof(uint32_t));
+    }
+    c->stats.d2h_bytes += (flags ? span : 0) + (counts ? 4 * span : 0);
+    return MSCAN_OK;
+  }
+  for (const LogPiece& p : pieces) {
+    if (flags) CU(cudaMemcpyAsync(flags + p.dst, c->d_flags + p.src, p.n, cudaMemcpyDeviceToHost, c->main_stream));
+    if (counts) CU(cudaMemcpyAsync(counts + p.dst, c->d_counts + p.src, p.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
+    c->stats.d2h_bytes += (flags ? p.n : 0) + (counts ? 4 * p.n : 0);
+  }
+  CU(cudaStreamSynchronize(c->main_stream));
+  return MSCAN_OK;
+}
+}  // namespace
+
 int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* counts, uint32_t cap, uint32_t* n_out) try {
   ApiTimer trace_(c, "mscan_collect");
   if (!c) return MSCAN_ERR_INVALID;
@@ -1890,14 +1936,13 @@ int mscan_collect(mscan_ctx* c, uint32_t video_id, uint8_t* flags, uint32_t* cou
   it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during the call", video_id);
   const Video& v = it->second;
+  std::vector<LogPiece> pieces;
+  pieces.reserve(v.extents.size());
   for (const Extent& e : v.extents) {
     if (e.vpos + e.n > cap) return fail(c, MSCAN_ERR_CAPACITY, "need room for %llu frames", (unsigned long long)v.n_frames);
-    if (flags) CU(cudaMemcpyAsync(flags + e.vpos, c->d_flags + e.start, e.n, cudaMemcpyDeviceToHost, c->main_stream));
-    if (counts) CU(cudaMemcpyAsync(counts + e.vpos, c->d_counts + e.start, e.n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
-    c->stats.d2h_bytes += (flags ? e.n : 0) + (counts ? 4 * e.n : 0);
+    pieces.push_back(LogPiece{e.start, e.n, e.vpos});
   }
-  CU(cudaStreamSynchronize(c->main_stream));
-  return MSCAN_OK;
+  return copy_log_pieces(c, pieces, flags, counts);
 } catch (...) {
   return on_exception(c);
 }
@@ -1917,17 +1962,12 @@ int mscan_collect_range(mscan_ctx* c, uint32_t video_id, uint64_t first, uint32_
   it = c->videos.find(video_id);
   if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during the call", video_id);
   const Video& v = it->second;
+  std::vector<LogPiece> pieces;
   for (const Extent& e : v.extents) {
     const uint64_t a = std::max<uint64_t>(first, e.vpos), b = std::min<uint64_t>(first + n, e.vpos + e.n);
-    if (a < b) {
-      const uint64_t src = e.start + (a - e.vpos), m = b - a, out = a - first;
-      if (flags) CU(cudaMemcpyAsync(flags + out, c->d_flags + src, m, cudaMemcpyDeviceToHost, c->main_stream));
-      if (counts) CU(cudaMemcpyAsync(counts + out, c->d_counts + src, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->main_stream));
-      c->stats.d2h_bytes += (flags ? m : 0) + (counts ? 4 * m : 0);
-    }
+    if (a < b) pieces.push_back(LogPiece{e.start + (a - e.vpos), b - a, a - first});
   }
-  CU(cudaStreamSynchronize(c->main_stream));
-  return MSCAN_OK;
+  return copy_log_pieces(c, pieces, flags, counts);
 } catch (...) {
   return on_exception(c);
 }
