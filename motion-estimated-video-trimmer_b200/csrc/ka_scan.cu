@@ -424,24 +424,12 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
                   cnt[cell] = 0;
                 }
               }
-              // the 32 cells of the flat word are a run of consecutive positions in row y0 that may continue in the
-              // next row(s): their activity bits (:282) go into the row-aligned bit-row words a segment at a time
-              uint32_t rest = __ballot_sync(0xffffffffu, valid && c >= vec_need);
-              if (lane == 0 && rest) {
-                uint32_t y = (kk * 32u) / (uint32_t)gw, x = kk * 32u - y * (uint32_t)gw, left = 32u;
-                while (rest) {
-                  const uint32_t n = min(left, (uint32_t)gw - x);
-                  const uint32_t seg = n >= 32u ? rest : (rest & ((1u << n) - 1u));
-                  if (seg) {
-                    const uint32_t w = x >> 5, sh = x & 31u;
-                    atomicOr(&brow[y * wpr + w], seg << sh);
-                    if (sh && (seg >> (32u - sh))) atomicOr(&brow[y * wpr + w + 1], seg >> (32u - sh));
-                  }
-                  rest = n >= 32u ? 0u : (rest >> n);
-                  left -= n;
-                  x = 0;
-                  ++y;
-                }
+              // (variants measured and dropped, profiles/r03_ka_epilogue_variants.log: one lane converting the word
+              // segment-wise — 3 to 7 % slower; marks per row-aligned word with direct ballot stores — 5 to 12 % slower,
+              // the extra index arithmetic on every vote costs more than an atomicOr for each of the few active cells)
+              if (valid && c >= vec_need) {  // :282
+                const uint32_t y = cell / (uint32_t)gw, x = cell - y * (uint32_t)gw;
+                atomicOr(&brow[y * wpr + (x >> 5)], 1u << (x & 31u));
               }
             }
           }
