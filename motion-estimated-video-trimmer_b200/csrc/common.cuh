@@ -26,18 +26,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait may suspend the thread up to the hinted time while the phase is incomplete (it returns as soon as the phase
-// completes): a waiting warp then leaves the issue slots to the warps that have work instead of spinning.
+// try_wait returns true once the phase with the given parity has completed. kHint: pass a suspend-time hint — the thread
+// may be suspended up to that long while the phase is incomplete, which suits the projected layouts (many resident warps,
+// issue-bound); the HBM-bound native layout polls without it (one CTA per SM at 4K: nothing hides a late wake-up).
 constexpr uint32_t kTryWaitHintNs = 20000;
+template <bool kHint = false>
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(kTryWaitHintNs)
-      : "memory");
+  if (kHint) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(kTryWaitHintNs)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
   return ok != 0;
 }
 // kSleep: poll with a short sleep, so that a starved warp does not burn issue slots the busy warps of the co-resident
@@ -45,8 +57,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // slots). The HBM-bound native layout keeps the plain spin: there the sleep only adds latency (8K: 7.1 → 6.8 TB/s).
 template <bool kSleep = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) {
+  if (mbar_try_wait<kSleep>(bar, parity)) return;
+  while (!mbar_try_wait<kSleep>(bar, parity)) {
     if (kSleep) __nanosleep(40);  // (an exponential back-off to 256 ns was tried: no gain at 1080p, −18 % on the dense 4K field)
   }
 }

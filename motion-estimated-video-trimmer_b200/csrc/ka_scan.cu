@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
   constexpr bool kMv8 = kLayout == (int)kLayoutMv8;
   constexpr bool kMvz = kLayout == (int)kLayoutMvz;
   constexpr uint32_t kStride = kPacked ? kPackedBytes : kRecBytes;
-  constexpr uint32_t kTile = kPacked ? kTileBytesPacked : kTileBytes;  // bytes per ring stage
+  constexpr uint32_t kTile = (kPacked && kConsWarps == 8) ? kTileBytesPacked : kTileBytes;  // bytes per ring stage (tile_bytes_for)
   constexpr int kCons = kConsWarps * 32;
   constexpr int kThreads = kCons + 32;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -494,8 +494,14 @@ __global__ void __launch_bounds__(kConsWarps * 32 + 32, kConsWarps == 8 ? 2 : 1)
 
 constexpr uint32_t kSmemReserve = 1024;  // per-CTA driver reservation
 
-uint32_t smem_for(uint32_t stages, uint32_t counter_bytes, uint32_t max_bit_words, bool packed) {
-  return stages * (uint32_t)(packed ? kTileBytesPacked : kTileBytes) + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
+// bytes per ring stage: half-size stages for the projected layouts with 8-warp CTAs (more CTAs per SM); 16-warp CTAs keep
+// the full stage — 16 warps x 64 records per trip would leave a 1 280-record stage two thirds empty on its second trip
+constexpr uint32_t tile_bytes_for(bool packed, uint32_t cons_warps) {
+  return (packed && cons_warps == 8) ? (uint32_t)kTileBytesPacked : (uint32_t)kTileBytes;
+}
+
+uint32_t smem_for(uint32_t stages, uint32_t counter_bytes, uint32_t max_bit_words, uint32_t tile_bytes) {
+  return stages * tile_bytes + stages * (uint32_t)sizeof(TileDesc) + 2 * stages * 8u +
          2 * max_bit_words * 4u + ((max_bit_words + 15u) & ~15u) + ((counter_bytes + 15u) & ~15u) + 128u;  // 2 bit-row buffers + vote marks
 }
 
@@ -506,10 +512,10 @@ uint32_t env_u32(const char* name) {
 }
 
 // largest ring depth in [lo, hi] that fits `ctas` CTAs per SM; 0 if none
-uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, uint32_t smem_optin, uint32_t lo, uint32_t hi, bool packed) {
+uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, uint32_t smem_optin, uint32_t lo, uint32_t hi, uint32_t tile_bytes) {
   const uint32_t sm_total = 228u * 1024u;
   for (uint32_t st = hi; st >= lo; --st) {
-    const uint32_t need = smem_for(st, counter_bytes, bit_words, packed);
+    const uint32_t need = smem_for(st, counter_bytes, bit_words, tile_bytes);
     if (need <= smem_optin && ctas * (need + kSmemReserve) <= sm_total) return st;
   }
   return 0;
@@ -519,24 +525,23 @@ uint32_t fit_stages(uint32_t ctas, uint32_t counter_bytes, uint32_t bit_words, u
 
 bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, bool packed, ScanPlan* plan) {
   const uint32_t b32 = max_cells * 4u, b16 = ((max_cells + 1u) / 2u) * 4u;
-  auto set = [&](uint32_t ctas, uint32_t st, uint32_t cnt16, uint32_t global_cnt) {
+  const uint32_t t8 = tile_bytes_for(packed, 8), t16 = tile_bytes_for(packed, 16);
+  auto set = [&](uint32_t ctas, uint32_t st, uint32_t cnt16, uint32_t global_cnt, uint32_t warps) {
     plan->stages = st;
     plan->ctas_per_sm = ctas;
     plan->cnt16 = cnt16;
     plan->global_cnt = global_cnt;
-    plan->cons_warps = ctas == 1 ? 16 : 8;
-    plan->smem_bytes = smem_for(st, global_cnt ? 0u : (cnt16 ? b16 : b32), max_bit_words, packed);
+    plan->cons_warps = warps;
+    plan->smem_bytes = smem_for(st, global_cnt ? 0u : (cnt16 ? b16 : b32), max_bit_words, tile_bytes_for(packed, warps));
     return true;
   };
   const uint32_t want_st = env_u32("MSCAN_KA_STAGES"), want_ctas = env_u32("MSCAN_KA_CTAS");
   if (want_st >= 2 && want_st <= 16 && want_ctas >= 1 && want_ctas <= 6) {
     const uint32_t c16 = env_u32("MSCAN_KA_CNT16") ? 1u : 0u;
-    if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st, packed)) {
-      set(want_ctas, want_st, c16, 0);
-      const uint32_t w = env_u32("MSCAN_KA_WARPS");
-      if (w == 8 || w == 16) plan->cons_warps = w;
-      return true;
-    }
+    uint32_t w = env_u32("MSCAN_KA_WARPS");
+    if (w != 8 && w != 16) w = want_ctas == 1 ? 16 : 8;
+    if (fit_stages(want_ctas, c16 ? b16 : b32, max_bit_words, smem_optin, want_st, want_st, tile_bytes_for(packed, w)))
+      return set(want_ctas, want_st, c16, 0, w);
   }
   uint32_t st;
   if (packed) {
@@ -544,26 +549,23 @@ bool scan_plan(uint32_t max_cells, uint32_t max_bit_words, uint32_t smem_optin, 
     // barriers), not by HBM, so the plan buys resident CTAs with ring depth — half-size stages (10 KB) are what lets a
     // fourth CTA fit at 1080p (sweep profiles/r03_ka_sweep_packed.log: 4 CTAs x 8 warps x 3 stages 556 G rec/s,
     // 5 x 8 x 2 517, 3 x 8 x 4 482; 16-warp CTAs are slower)
-    if ((st = fit_stages(4, b16, max_bit_words, smem_optin, 3, 3, packed))) return set(4, st, 1, 0);
-    if ((st = fit_stages(3, b16, max_bit_words, smem_optin, 2, 4, packed))) return set(3, st, 1, 0);
-    if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 2, 4, packed))) {
-      set(2, st, 1, 0);
-      plan->cons_warps = 16;
-      return true;
-    }
+    if ((st = fit_stages(4, b16, max_bit_words, smem_optin, 3, 3, t8))) return set(4, st, 1, 0, 8);
+    if ((st = fit_stages(3, b16, max_bit_words, smem_optin, 2, 4, t8))) return set(3, st, 1, 0, 8);
+    // 4K grids: two 16-warp CTAs with two full-size stages each (356 G rec/s on the dense field; four half-size stages 293)
+    if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 2, 2, t16))) return set(2, st, 1, 0, 16);
   }
   // 1-4: two CTAs per SM; a 4-stage ring (160 KB in flight per SM) measures ~1.3 % faster than 3 stages
   // (tools/ka_sweep.py), so 16-bit counters are preferred when they are what makes the 4th stage fit
-  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4, packed))) return set(2, st, 0, 0);
-  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 4, 4, packed))) return set(2, st, 1, 0);
-  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 3, 3, packed))) return set(2, st, 0, 0);
-  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 3, 3, packed))) return set(2, st, 1, 0);
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 4, 4, t8))) return set(2, st, 0, 0, 8);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 4, 4, t8))) return set(2, st, 1, 0, 8);
+  if ((st = fit_stages(2, b32, max_bit_words, smem_optin, 3, 3, t8))) return set(2, st, 0, 0, 8);
+  if ((st = fit_stages(2, b16, max_bit_words, smem_optin, 3, 3, t8))) return set(2, st, 1, 0, 8);
   // 5-7: one CTA per SM with 16 consumer warps and as deep a ring as fits (4K: u16 counters give 7 stages)
-  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 6, 8, packed))) return set(1, st, 0, 0);
-  if ((st = fit_stages(1, b16, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 1, 0);
-  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 0, 0);
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 6, 8, t16))) return set(1, st, 0, 0, 16);
+  if ((st = fit_stages(1, b16, max_bit_words, smem_optin, 2, 8, t16))) return set(1, st, 1, 0, 16);
+  if ((st = fit_stages(1, b32, max_bit_words, smem_optin, 2, 8, t16))) return set(1, st, 0, 0, 16);
   // 8: counters in global memory (8K and larger)
-  if ((st = fit_stages(1, 0, max_bit_words, smem_optin, 2, 8, packed))) return set(1, st, 0, 1);
+  if ((st = fit_stages(1, 0, max_bit_words, smem_optin, 2, 8, t16))) return set(1, st, 0, 1, 16);
   return false;
 }
 
