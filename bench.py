@@ -441,7 +441,7 @@ def run_gpu(args):
 
     import motionscan as ms
 
-    from motionscan.dist import Dist, throughput
+    from motionscan.dist import Dist, strong_share, throughput, video_pieces
 
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -470,8 +470,7 @@ def run_gpu(args):
     else:
         total_frames_all = fixed_frames if fixed_frames is not None else frames_for_records(ctx, spec, args.records, sh, stream)
     if strong:  # one stream, rank g scans frames [g·F/G, (g+1)·F/G)  
-        frame0 = total_frames_all * rank // world
-        n_frames = total_frames_all * (rank + 1) // world - frame0
+        frame0, n_frames = strong_share(total_frames_all, world, rank)
     else:
         frame0, n_frames = 0, total_frames_all
     fpv = spec.frames_per_video
@@ -487,8 +486,7 @@ def run_gpu(args):
 
     def video_offsets(f0, n):
         """Local frame offsets of the videos (pieces of videos at the ends of a strong-scaling share) in [f0, f0+n)."""
-        inner = vstarts[(vstarts > f0) & (vstarts < f0 + n)] - f0
-        return np.array(sorted({0, n} | {int(x) for x in inner}), dtype=np.uint64)
+        return np.array(video_pieces(vstarts, f0, n), dtype=np.uint64)
 
     voff = video_offsets(frame0, n_frames)
     n_videos = len(voff) - 1

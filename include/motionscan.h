@@ -298,7 +298,9 @@ int mscan_offsets_from_counts(mscan_ctx* ctx, const uint32_t* d_rec_count, uint3
                               uint64_t* d_rec_off, void* stream);
 /* K-A on device memory. d_recs: 16-byte aligned; d_rec_off[n_frames+1] record indices into d_recs;
  * d_frame_geom: per-frame index into geoms[] or NULL (all frames use geoms[0]).
- * Asynchronous on `stream` (NULL → the context's scan stream). */
+ * Asynchronous on `stream` (NULL → the context's scan stream), with two exceptions that synchronise the device and are
+ * therefore not legal under stream capture: a call whose geoms[] differ from the previous call's (the table is
+ * re-uploaded), and grids so large that the vote counters live in global memory (beyond 16 CTAs of shared memory). */
 int mscan_scan_device(mscan_ctx* ctx, const mscan_mv* d_recs, const uint64_t* d_rec_off,
                       const uint32_t* d_frame_geom, const mscan_geometry* geoms, uint32_t n_geoms,
                       uint32_t n_frames, uint8_t* d_flags, uint32_t* d_full_counts, void* stream);

@@ -76,3 +76,17 @@ def shard_videos(n_videos: int, world: int, rank: int) -> list[int]:
 def throughput(units_per_rank_sum: float, steps: int, max_ms_over_ranks: float) -> float:
     """Whole-job units/s: everything all ranks processed ÷ the slowest rank's time."""
     return units_per_rank_sum * steps / (max_ms_over_ranks * 1e-3)
+
+
+def strong_share(n_frames: int, world: int, rank: int) -> tuple[int, int]:
+    """Strong scaling of ONE stream: rank g scans frames [g·F/G, (g+1)·F/G) — contiguous,
+    disjoint, covering, sizes within one frame of each other. Returns (first_frame, n)."""
+    a = n_frames * rank // world
+    return a, n_frames * (rank + 1) // world - a
+
+
+def video_pieces(video_starts, first_frame: int, n: int):
+    """Local frame offsets at which videos (or pieces of videos cut by a share's ends) begin inside the share
+    [first_frame, first_frame + n), plus n: what K-C receives as video boundaries. video_starts: global start frames."""
+    inner = sorted({int(s) - first_frame for s in video_starts if first_frame < int(s) < first_frame + n})
+    return [0] + inner + [n]

@@ -93,3 +93,26 @@ def test_shard_videos_partition():
             parts = [shard_videos(n, world, r) for r in range(world)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
+
+
+def test_strong_scaling_shares_and_video_pieces():
+    """bench.py --scaling strong: one stream cut into contiguous frame shares; the videos a share cuts
+    through become pieces, and the pieces of all shares tile every video exactly once."""
+    from motionscan.dist import strong_share, video_pieces
+
+    for total in (1, 7, 61275, 100153):
+        for world in (1, 2, 3, 4, 8):
+            shares = [strong_share(total, world, r) for r in range(world)]
+            assert shares[0][0] == 0 and sum(n for _, n in shares) == total
+            assert all(shares[r][0] + shares[r][1] == shares[r + 1][0] for r in range(world - 1))
+            assert max(n for _, n in shares) - min(n for _, n in shares) <= 1
+    starts = list(range(0, 100153 + 18000, 18000))  # 10-minute videos
+    covered = []
+    for r in range(8):
+        f0, n = strong_share(100153, 8, r)
+        cuts = video_pieces(starts, f0, n)
+        assert cuts[0] == 0 and cuts[-1] == n and cuts == sorted(set(cuts))
+        covered += [(f0 + a, f0 + b) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert covered[0][0] == 0 and covered[-1][1] == 100153
+    assert all(a[1] == b[0] for a, b in zip(covered[:-1], covered[1:]))          # the pieces tile the stream
+    assert all(a // 18000 == (b - 1) // 18000 for a, b in covered)                # and none spans two videos
