@@ -594,6 +594,7 @@ def run_gpu(args):
     #   projected       whole videos of native records resident in host DRAM, one mscan_submit each: the library's
     #                   worker pool projects them (bound by reading 40 B/record from DRAM)
     #   packed_pinned   the caller hands over records it projected itself beforehand; only DMA + kernels are timed
+    #   elided_pinned   same with the caller's own static-elided encoding (mscan_elide_records → mscan_submit_elided)
     # `e2e.value` is the best of the modes that start from native host records (the first three).
     # the same frame count the reference arm derives (sample_frames): both arms scan the same host sample
     e2e_frames = min(sample_frames(args, spec, ms, max(1, len(my_cpus))), n_frames)
@@ -615,6 +616,13 @@ def run_gpu(args):
     pack_threads = max(1, len(my_cpus))
     ctx.set_pack_threads(pack_threads)
     src8 = np.array(h_r8)  # the stand-in decoders' compact input lives in ordinary pageable memory
+    # elided_pinned: the caller's own static-elided encoding of the sample in pinned memory (link-saturated run of that form)
+    h_enc = z_off = z_te = z_tiles = None
+    if "elided_pinned" in args.e2e_modes.split(","):
+        z_bound = sum(int(ms.lib().mscan_elide_bound(int(x))) for x in h_cnt)
+        h_enc = ctx.pinned_array(z_bound + 16, np.uint8)
+        z_enc, z_off, z_te = ms.elide_frames(h_recs, e_off, out=h_enc)
+        z_tiles = np.concatenate([[0], np.cumsum((h_cnt.astype(np.int64) + 1023) // 1024)])
 
     def tail(vids):
         out = [ctx.collect(v) for v in vids]
@@ -647,7 +655,9 @@ def run_gpu(args):
             return ordered, segs
         for v in e_vids:
             a, b = int(e_voff[v]), int(e_voff[v + 1])
-            if mode == "packed_pinned":
+            if mode == "elided_pinned":
+                ctx.submit_elided(v, h_pts[a:b], h_cnt[a:b], h_enc, z_off[a : b + 1], z_te[int(z_tiles[a]) : int(z_tiles[b])])
+            elif mode == "packed_pinned":
                 ctx.submit_packed_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_r8.ctypes.data + 8 * int(e_off[a]))
             else:
                 ctx.submit_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_recs.ctypes.data + REC_BYTES * int(e_off[a]))
@@ -656,7 +666,7 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     modes = {}
     seg_ref = None
-    all_modes = ("producers", "producers_elided", "native_inplace", "projected", "packed_pinned")
+    all_modes = ("producers", "producers_elided", "native_inplace", "projected", "packed_pinned", "elided_pinned")
     run_modes = [m for m in all_modes if m in args.e2e_modes.split(",")] or list(all_modes)
     for mode in run_modes:
         # producers: mscan_mv8 on the wire (STAGING_PACK); producers_elided: the library's default for a decode thread's
@@ -722,7 +732,11 @@ def run_gpu(args):
         pm = modes[name]
         cap = modes["packed_pinned"]["value"] if "packed_pinned" in modes else world * pcie_gbs * 1e9 / 8.0
         cap_how = "the rate measured in this run with the link saturated (packed_pinned: 8 B/record, DMA + K-A + tail by wall clock)"
-        if name == "producers_elided":  # fewer bytes per record on the same link: the measured link-bound rate scales with the wire size
+        if name == "producers_elided" and "elided_pinned" in modes:
+            cap = modes["elided_pinned"]["value"]
+            cap_how = ("the rate measured in this run with the link saturated in the same wire form (elided_pinned: the caller's own "
+                       "static-elided encoding in pinned memory, DMA + K-A + tail by wall clock)")
+        elif name == "producers_elided":  # fewer bytes per record on the same link: the measured link-bound rate scales with the wire size
             cap = cap * 8.0 / max(pm["wire_bytes_per_record"], 1e-9)
             cap_how += f", scaled by 8 / {pm['wire_bytes_per_record']:.2f} B per record measured on the wire in the static-elided form"
         pm["value_wall_incl_decode_standin"] = pm["value"]
@@ -879,6 +893,8 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     ctx.host_free(h_recs.ctypes.data)
+    if h_enc is not None:
+        ctx.host_free(h_enc.ctypes.data)
     ctx.host_free(h_r8.ctypes.data)
     ctx.host_free(h_pts.ctypes.data)
     ctx.close()
@@ -899,7 +915,7 @@ def main():
     ap.add_argument("--e2e-records", type=float, default=6e7, help="records of the host-resident sample both arms scan (~2.4 GB pinned)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="override: frames of the host sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-modes", default="producers,producers_elided,native_inplace,projected,packed_pinned", help="experiments: subset of the e2e modes to run")
+    ap.add_argument("--e2e-modes", default="producers,producers_elided,native_inplace,projected,packed_pinned,elided_pinned", help="experiments: subset of the e2e modes to run")
     ap.add_argument("--feed-batch", type=int, default=1, help="frames per mscan_submit of the producer stand-ins (1 = per frame, like check_frame)")
     ap.add_argument("--feed-threads", type=int, default=0, help="producer stand-in threads per rank (0 = one per CPU of the rank)")
     ap.add_argument("--ref-repeats", type=int, default=5, help="--impl reference: independent runs (value = median)")

@@ -15,6 +15,8 @@
  *   mscan_submit            <- the per-frame call `check_frame(frame)` src/motion_scanner.cpp:376
  *                              (decl include/motion_trim/motion_scanner.hpp:106), batched
  *   mscan_submit_device     <- same call site, records already in device memory (no host staging)
+ *   mscan_submit_elided / mscan_elide_records
+ *                           <- same call site; the caller's own static-elided encoding of the records
  *   mscan_submit_packed / mscan_pack_records / mscan_mv8
  *                           <- same call site; the record is the byte range [6,14) of AVMotionVector,
  *                              i.e. exactly the fields read at src/motion_scanner.cpp:243-256
@@ -240,6 +242,15 @@ int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out);
 int mscan_elide_records(const mscan_mv* recs, uint32_t n, void* out, size_t cap, uint32_t* tile_end16, uint32_t tile_cap,
                         size_t* bytes_out);
 size_t mscan_elide_bound(uint32_t n);
+/* Append frames the caller has already put into the static-elided form — a decode thread that runs mscan_elide_records
+ * on its cache-hot side data and keeps the result in pinned memory. enc: the frames' encodings, each 16-byte aligned;
+ * enc_off[n_frames + 1]: byte offset of every frame's encoding in enc (frames without records have none);
+ * tile_end16: for all tiles of all frames in order, what mscan_elide_records returned (ends in 16-byte units from the
+ * start of the frame's own encoding). Pinned memory is DMA'd in place (lifetime rule of mscan_submit), pageable memory is
+ * copied into the pinned ring. MSCAN_ERR_UNSUPPORTED on contexts whose largest grid needs the cluster kernel. */
+int mscan_submit_elided(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, const double* pts,
+                        const uint32_t* rec_count, const void* enc, const uint64_t* enc_off,
+                        const uint32_t* tile_end16, uint64_t* first_frame_out);
 /* MSCAN_STAGING_*; default AUTO. */
 int mscan_set_staging_mode(mscan_ctx* ctx, int mode);
 /* Threads (including the caller) that project one large submit; 0 → as many as the process may run on

@@ -1333,37 +1333,189 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
   return rc;
 }
 
-// mscan_submit under MSCAN_STAGING_ELIDE: the calling thread encodes its native records as mvz (host_project.cpp:
-// static macroblocks shrink to 4 bytes + a mask bit) into a private scratch, then reserves exactly the encoded size,
-// copies it into the pinned ring outside the mutex and commits. The caller (submit_impl) has released the mutex.
-static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                        const uint8_t* src, uint64_t* first_frame_out) {
+// Places frames that are already in the static-elided form (mvz, host_project.cpp) into the slab ring: whole frames,
+// in as many reservations as slab / log / directory room demands; the bytes are moved outside the mutex (streaming copy
+// into the pinned ring, or DMA'd in place out of pinned caller memory) and committed.
+struct ElidedPlacer {
+  mscan_ctx* c;
+  uint32_t video_id;
+  uint32_t n_frames;         // frames of the whole submit call
+  uint64_t* first_frame_out;
   // The call's video-local indices [vbase, vbase + n_frames) are reserved in the SAME critical section that places its
   // first frames: per-frame submits from many decode threads then get video order == log order, and the video stays
   // one extent instead of one per frame.
   uint64_t vbase = 0;
   bool have_vbase = false;
-  thread_local std::vector<uint8_t> scratch;       // one encoded piece
-  thread_local std::vector<uint32_t> tile_end;     // per tile of the piece: end, 16-byte units from the piece start
-  thread_local std::vector<uint32_t> frame_tile;   // per frame of the piece (+1): index of its first tile
-  thread_local std::vector<uint64_t> frame_end;    // per frame of the piece (+1): end byte offset in the piece
-  std::unique_lock<std::mutex> lk(c->mu, std::defer_lock);
-  uint32_t f = 0;
-  uint64_t src_rec = 0;
-  auto give_back = [&](uint32_t placed) {  // like submit_impl's Rollback
+  std::unique_lock<std::mutex> lk;
+
+  ElidedPlacer(mscan_ctx* ctx, uint32_t vid, uint32_t n, uint64_t* first) : c(ctx), video_id(vid), n_frames(n), first_frame_out(first), lk(ctx->mu, std::defer_lock) {}
+
+  void give_back(uint32_t placed) {  // like submit_impl's Rollback
     if (!have_vbase) return;
     if (!lk.owns_lock()) lk.lock();
     auto it = c->videos.find(video_id);
     if (it != c->videos.end() && it->second.n_frames == vbase + n_frames) it->second.n_frames = vbase + placed;
-  };
+    lk.unlock();
+  }
+
+  // One piece: nf frames starting at frame f0 of the call. data: the piece's encoded bytes; frame_end[i + 1]: end byte
+  // offset of frame i in data (frame_end[0] == 0); frame_tile[i]: index of frame i's first tile in tile_end (size nf + 1);
+  // tile_end[t]: end of tile t in 16-byte units from the start of data. in_place: data is pinned caller memory.
+  int place(uint32_t f0, uint32_t nf, const double* pts, const uint32_t* rec_count, const uint8_t* data, const uint64_t* frame_end,
+            const uint32_t* frame_tile, const uint32_t* tile_end, bool in_place) {
+    uint32_t i = 0;
+    while (i < nf) {
+      lock_briefly(lk);
+      auto it = c->videos.find(video_id);
+      if (it == c->videos.end()) {
+        lk.unlock();
+        return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+      }
+      Video& v = it->second;
+      if (!have_vbase) {
+        vbase = v.n_frames;
+        v.n_frames += n_frames;
+        have_vbase = true;
+        if (first_frame_out) *first_frame_out = vbase;
+      }
+      Slab* s = &c->slabs[c->cur];
+      int rc = MSCAN_OK;
+      if (s->frames > s->seg_frame0 && (s->fmt != kLayoutMvz || s->staged == in_place)) rc = launch_segment(c, *s);
+      if (!rc && c->log_head >= c->log_limit) {
+        rc = launch_segment(c, *s);
+        if (!rc && !log_find_space(c))
+          rc = fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos); close videos or create a larger context",
+                    (unsigned long long)c->log_cap);
+      }
+      if (rc) {
+        lk.unlock();
+        give_back(f0 + i);
+        return rc;
+      }
+      const bool opens = s->frames == s->seg_frame0;
+      const uint64_t b0 = frame_end[i], log_room = c->log_limit - c->log_head;
+      uint32_t take = 0;
+      while (i + take < nf && s->frames + take < c->slab_frames && take < log_room) {
+        const uint64_t nb = frame_end[(size_t)i + take + 1] - b0;
+        const uint32_t tiles = frame_tile[(size_t)i + take + 1] - frame_tile[i];
+        if (s->bytes + nb > c->slab_bytes) break;
+        if ((uint64_t)s->dir_slots + (opens ? 1u : 0u) + tiles + 1u > c->slab_dir_cap) break;
+        ++take;
+      }
+      if (take == 0) {
+        if (s->frames == 0) rc = fail(c, MSCAN_ERR_CAPACITY, "frame with %u records exceeds the slab size (%llu bytes)", rec_count[i],
+                                      (unsigned long long)c->slab_bytes);
+        else rc = flush_locked(c);
+        lk.unlock();
+        if (rc) {
+          give_back(f0 + i);
+          return rc;
+        }
+        continue;
+      }
+      const uint64_t nbytes = frame_end[(size_t)i + take] - b0;
+      if (!in_place && nbytes && !s->h_recs) {
+        cudaError_t e = use_device(c);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+          lk.unlock();
+          give_back(f0 + i);
+          return fail(c, MSCAN_ERR_NOMEM, "cudaHostAlloc of the staging slab failed: %s", cudaGetErrorString(e));
+        }
+      }
+      if (opens) {
+        s->seg_log_base = c->log_head;
+        s->fmt = (uint8_t)kLayoutMvz;
+        s->seg_dir0 = s->dir_slots;
+        s->h_tile_dir[s->dir_slots++] = 0;  // tile 0 of the segment starts at its base
+        std::lock_guard<std::mutex> issue(c->issue_mu);
+        s->staged = !in_place;
+        s->copy_head = s->seg_byte0;
+      }
+      const uint64_t off = s->bytes;
+      // piece-relative 16-byte units → segment-relative: frame i's first tile starts where the segment's last one ended
+      const uint32_t rel16 = (uint32_t)((off - s->seg_byte0) >> 4) - (uint32_t)(b0 >> 4);
+      const uint32_t tiles_before = s->dir_slots - s->seg_dir0 - 1;
+      uint64_t r = s->seg_recs, take_recs = 0;
+      const uint32_t slot = s->seg_slot0 + (s->frames - s->seg_frame0);
+      for (uint32_t k = 0; k < take; ++k) {
+        s->h_rec_off[slot + k] = r;
+        r += rec_count[i + k];
+        take_recs += rec_count[i + k];
+        s->h_geom[s->frames + k] = v.geom;
+        s->h_pts[s->frames + k] = pts[i + k];
+        s->h_frame_tile0[s->frames + k] = tiles_before + (frame_tile[(size_t)i + k] - frame_tile[i]);
+      }
+      for (uint32_t t = frame_tile[i]; t < frame_tile[(size_t)i + take]; ++t) s->h_tile_dir[s->dir_slots++] = tile_end[t] + rel16;
+      const uint64_t log_at = c->log_head, vpos = vbase + f0 + i;
+      if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == log_at && v.extents.back().vpos + v.extents.back().n == vpos)
+        v.extents.back().n += take;
+      else v.extents.push_back(Extent{log_at, take, vpos});
+      v.slab_epoch[c->cur] = s->epoch;
+      c->log_head += take;
+      s->frames += take;
+      s->seg_recs += take_recs;
+      s->bytes += nbytes;
+      const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
+      const uint64_t my_epoch = s->epoch;
+      if (nbytes) {
+        if (in_place) s->writers.fetch_add(1, std::memory_order_relaxed);
+        else
+          for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k) s->pend[k * kPendStride].fetch_add(1, std::memory_order_relaxed);
+        s->reserved_end.store(s->bytes, std::memory_order_release);
+      }
+      lk.unlock();
+      if (nbytes) {
+        if (in_place) {
+          std::lock_guard<std::mutex> issue(c->issue_mu);
+          cudaError_t e = use_device(c);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(s->d_recs + off, data + b0, nbytes, cudaMemcpyHostToDevice, s->stream);
+          if (e != cudaSuccess) rc = MSCAN_ERR_CUDA;
+          c->a_h2d_bytes.fetch_add(nbytes, std::memory_order_relaxed);
+        } else {
+          stream_copy(data + b0, s->h_recs + off, nbytes);
+        }
+        commit_fill(c, *s, !in_place, off, nbytes);
+        if (rc) {
+          give_back(f0 + i);
+          return fail(c, rc, "cudaMemcpyAsync of pinned elided records failed");
+        }
+      }
+      i += take;
+      if (slab_full) {
+        lock_briefly(lk);
+        if (&c->slabs[c->cur] == s && s->epoch == my_epoch) rc = flush_locked(c);
+        lk.unlock();
+        if (rc) {
+          give_back(f0 + i);
+          return rc;
+        }
+      }
+    }
+    return MSCAN_OK;
+  }
+};
+
+// mscan_submit under MSCAN_STAGING_ELIDE (and AUTO for small pageable submits): the calling thread encodes its native
+// records as mvz into a private scratch, piece by piece, and places each piece. The caller (submit_impl) has released
+// the mutex.
+static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                        const uint8_t* src, uint64_t* first_frame_out) {
+  thread_local std::vector<uint8_t> scratch;       // one encoded piece
+  thread_local std::vector<uint32_t> tile_end;     // per tile of the piece: end, 16-byte units from the piece start
+  thread_local std::vector<uint32_t> frame_tile;   // per frame of the piece (+1): index of its first tile
+  thread_local std::vector<uint64_t> frame_end;    // per frame of the piece (+1): end byte offset in the piece
+  ElidedPlacer placer(c, video_id, n_frames, first_frame_out);
+  uint32_t f = 0;
+  uint64_t src_rec = 0;
   while (f < n_frames) {
-    // ---- 1. encode a piece outside the mutex: frames [f, g) with at most kPoolMinRecs records (one frame at least)
+    // encode a piece outside the mutex: frames [f, g) with at most kPoolMinRecs records (one frame at least)
     uint32_t g = f;
     uint64_t piece_recs = 0;
     while (g < n_frames && (g == f || piece_recs + rec_count[g] <= kPoolMinRecs)) piece_recs += rec_count[g++];
     const uint32_t nf = g - f;
     if (piece_recs && !src) {
-      give_back(f);
+      placer.give_back(f);
       return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
     }
     const auto t0 = std::chrono::steady_clock::now();
@@ -1393,119 +1545,8 @@ static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
     c->a_records_projected.fetch_add(piece_recs, std::memory_order_relaxed);
     c->a_records_elided.fetch_add(piece_recs, std::memory_order_relaxed);
     c->a_elided_bytes.fetch_add(at, std::memory_order_relaxed);
-    // ---- 2. place the piece's frames: whole frames, in as many reservations as slab / log / directory room demands
-    uint32_t i = 0;
-    uint64_t rec_i = 0;  // records of the piece's frames [0, i)
-    while (i < nf) {
-      lock_briefly(lk);
-      auto it = c->videos.find(video_id);
-      if (it == c->videos.end()) return fail(c, MSCAN_ERR_INVALID, "video %u was closed during a submit", video_id);
-      Video& v = it->second;
-      if (!have_vbase) {
-        vbase = v.n_frames;
-        v.n_frames += n_frames;
-        have_vbase = true;
-        if (first_frame_out) *first_frame_out = vbase;
-      }
-      Slab* s = &c->slabs[c->cur];
-      if (s->frames > s->seg_frame0 && (s->fmt != kLayoutMvz || !s->staged)) {
-        int rc = launch_segment(c, *s);
-        if (rc) return give_back(f + i), rc;
-      }
-      if (c->log_head >= c->log_limit) {
-        int rc = launch_segment(c, *s);
-        if (rc) return give_back(f + i), rc;
-        if (!log_find_space(c)) {
-          give_back(f + i);
-          return fail(c, MSCAN_ERR_CAPACITY, "frame log full (%llu frames, all owned by open videos); close videos or create a larger context",
-                      (unsigned long long)c->log_cap);
-        }
-      }
-      const bool opens = s->frames == s->seg_frame0;
-      const uint64_t b0 = frame_end[i], log_room = c->log_limit - c->log_head;
-      uint32_t take = 0;
-      while (i + take < nf && s->frames + take < c->slab_frames && take < log_room) {
-        const uint64_t nb = frame_end[(size_t)i + take + 1] - b0;
-        const uint32_t tiles = frame_tile[(size_t)i + take + 1] - frame_tile[i];
-        if (s->bytes + nb > c->slab_bytes) break;
-        if ((uint64_t)s->dir_slots + (opens ? 1u : 0u) + tiles + 1u > c->slab_dir_cap) break;
-        ++take;
-      }
-      if (take == 0) {
-        if (s->frames == 0) {
-          give_back(f + i);
-          return fail(c, MSCAN_ERR_CAPACITY, "frame with %u records exceeds the slab size (%llu bytes)", rec_count[f + i],
-                      (unsigned long long)c->slab_bytes);
-        }
-        int rc = flush_locked(c);
-        lk.unlock();
-        if (rc) return give_back(f + i), rc;
-        continue;
-      }
-      if (opens) {
-        s->seg_log_base = c->log_head;
-        s->fmt = (uint8_t)kLayoutMvz;
-        s->seg_dir0 = s->dir_slots;
-        s->h_tile_dir[s->dir_slots++] = 0;  // tile 0 of the segment starts at its base
-        std::lock_guard<std::mutex> issue(c->issue_mu);
-        s->staged = true;
-        s->copy_head = s->seg_byte0;
-      }
-      const uint64_t nbytes = frame_end[(size_t)i + take] - b0;
-      if (nbytes && !s->h_recs) {
-        cudaError_t e = use_device(c);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->h_recs, c->slab_bytes, cudaHostAllocDefault);
-        if (e != cudaSuccess) {
-          give_back(f + i);
-          return fail(c, MSCAN_ERR_NOMEM, "cudaHostAlloc of the staging slab failed: %s", cudaGetErrorString(e));
-        }
-      }
-      const uint64_t off = s->bytes;
-      // piece-relative 16-byte units → segment-relative: frame i's first tile starts where the segment's last one ended
-      const uint32_t rel16 = (uint32_t)((off - s->seg_byte0) >> 4) - (uint32_t)(b0 >> 4);
-      const uint32_t tiles_before = s->dir_slots - s->seg_dir0 - 1;
-      uint64_t r = s->seg_recs, take_recs = 0;
-      const uint32_t slot = s->seg_slot0 + (s->frames - s->seg_frame0);
-      for (uint32_t k = 0; k < take; ++k) {
-        s->h_rec_off[slot + k] = r;
-        r += rec_count[f + i + k];
-        take_recs += rec_count[f + i + k];
-        s->h_geom[s->frames + k] = v.geom;
-        s->h_pts[s->frames + k] = pts[f + i + k];
-        s->h_frame_tile0[s->frames + k] = tiles_before + (frame_tile[(size_t)i + k] - frame_tile[i]);
-      }
-      for (uint32_t t = frame_tile[i]; t < frame_tile[(size_t)i + take]; ++t) s->h_tile_dir[s->dir_slots++] = tile_end[t] + rel16;
-      const uint64_t log_at = c->log_head, vpos = vbase + f + i;
-      if (!v.extents.empty() && v.extents.back().start + v.extents.back().n == log_at && v.extents.back().vpos + v.extents.back().n == vpos)
-        v.extents.back().n += take;
-      else v.extents.push_back(Extent{log_at, take, vpos});
-      v.slab_epoch[c->cur] = s->epoch;
-      c->log_head += take;
-      s->frames += take;
-      s->seg_recs += take_recs;
-      s->bytes += nbytes;
-      const bool slab_full = s->frames == c->slab_frames || s->bytes + 64 * 1024 > c->slab_bytes;
-      const uint64_t my_epoch = s->epoch;
-      if (nbytes) {
-        for (uint64_t k = off >> c->win_shift; k <= (off + nbytes - 1) >> c->win_shift; ++k) s->pend[k * kPendStride].fetch_add(1, std::memory_order_relaxed);
-        s->reserved_end.store(s->bytes, std::memory_order_release);
-      }
-      lk.unlock();
-      if (nbytes) {
-        stream_copy(scratch.data() + b0, s->h_recs + off, nbytes);
-        commit_fill(c, *s, true, off, nbytes);
-      }
-      i += take;
-      rec_i += take_recs;
-      if (slab_full) {
-        lock_briefly(lk);
-        int rc = MSCAN_OK;
-        if (&c->slabs[c->cur] == s && s->epoch == my_epoch) rc = flush_locked(c);
-        lk.unlock();
-        if (rc) return give_back(f + i), rc;
-      }
-    }
-    (void)rec_i;
+    int rc = placer.place(f, nf, pts + f, rec_count + f, scratch.data(), frame_end.data(), frame_tile.data(), tile_end.data(), false);
+    if (rc) return rc;
     f = g;
     src_rec += piece_recs;
   }
@@ -1817,6 +1858,65 @@ int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out) {
   if (reinterpret_cast<uintptr_t>(out) & 7u) return MSCAN_ERR_INVALID;
   project_records(reinterpret_cast<const uint8_t*>(recs), n, reinterpret_cast<uint64_t*>(out));
   return MSCAN_OK;
+}
+
+int mscan_submit_elided(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                        const void* enc, const uint64_t* enc_off, const uint32_t* tile_end16, uint64_t* first_frame_out) try {
+  ApiTimer trace_(c, "mscan_submit_elided");
+  if (!c) return MSCAN_ERR_INVALID;
+  if (n_frames == 0) {
+    if (first_frame_out) {
+      std::lock_guard<std::mutex> lk(c->mu);
+      auto it0 = c->videos.find(video_id);
+      *first_frame_out = it0 == c->videos.end() ? 0 : it0->second.n_frames;
+    }
+    return MSCAN_OK;
+  }
+  if (!pts || !rec_count || !enc_off) return fail(c, MSCAN_ERR_INVALID, "null pts/rec_count/enc_off");
+  const uint8_t* data = static_cast<const uint8_t*>(enc);
+  const uint64_t total_bytes = enc_off[n_frames] - enc_off[0];
+  if (total_bytes && (!enc || !tile_end16)) return fail(c, MSCAN_ERR_INVALID, "null enc/tile_end16 with non-empty frames");
+  if ((reinterpret_cast<uintptr_t>(data) + enc_off[0]) & 15u) return fail(c, MSCAN_ERR_INVALID, "elided frames must be 16-byte aligned");
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->videos.count(video_id)) return fail(c, MSCAN_ERR_INVALID, "video %u is not open", video_id);
+    if (c->plan_packed.cluster || c->plan_packed.global_cnt)
+      return fail(c, MSCAN_ERR_UNSUPPORTED, "the static-elided form is not read by the cluster kernel (grids beyond one CTA's shared memory)");
+  }
+  // piece-relative tables (one piece = the whole call)
+  std::vector<uint64_t> frame_end((size_t)n_frames + 1);
+  std::vector<uint32_t> frame_tile((size_t)n_frames + 1), tile_end;
+  uint32_t nt = 0;
+  frame_end[0] = 0;
+  for (uint32_t i = 0; i < n_frames; ++i) {
+    if (enc_off[i + 1] < enc_off[i] || ((enc_off[i] - enc_off[0]) & 15u)) return fail(c, MSCAN_ERR_INVALID, "enc_off must be non-decreasing multiples of 16");
+    const uint32_t tiles = (rec_count[i] + kMvzTileRecs - 1) / kMvzTileRecs;
+    const uint64_t rel = enc_off[i] - enc_off[0], bytes = enc_off[i + 1] - enc_off[i];
+    frame_tile[i] = nt;
+    for (uint32_t t = 0; t < tiles; ++t) {
+      const uint64_t end = (uint64_t)tile_end16[nt + t] << 4;  // from the start of the frame's encoding
+      if (end > bytes || (t && tile_end16[nt + t] < tile_end16[nt + t - 1])) return fail(c, MSCAN_ERR_INVALID, "tile ends of frame %u do not fit its encoding", i);
+      tile_end.push_back((uint32_t)((rel + end) >> 4));
+    }
+    if (tiles && ((uint64_t)tile_end16[nt + tiles - 1] << 4) != bytes) return fail(c, MSCAN_ERR_INVALID, "frame %u: the last tile must end at the frame's end", i);
+    if (!tiles && bytes) return fail(c, MSCAN_ERR_INVALID, "frame %u has no records but %llu encoded bytes", i, (unsigned long long)bytes);
+    nt += tiles;
+    frame_end[(size_t)i + 1] = rel + bytes;
+  }
+  frame_tile[n_frames] = nt;
+  bool pinned = false;
+  if (total_bytes) {
+    pinned = pinned_ranges().contains(data + enc_off[0], total_bytes);
+    if (!pinned && total_bytes >= kAttrQueryBytes) pinned = is_pinned(data + enc_off[0]);
+  }
+  uint64_t recs = 0;
+  for (uint32_t i = 0; i < n_frames; ++i) recs += rec_count[i];
+  c->a_records_elided.fetch_add(recs, std::memory_order_relaxed);
+  c->a_elided_bytes.fetch_add(total_bytes, std::memory_order_relaxed);
+  ElidedPlacer placer(c, video_id, n_frames, first_frame_out);
+  return placer.place(0, n_frames, pts, rec_count, data + enc_off[0], frame_end.data(), frame_tile.data(), tile_end.data(), pinned);
+} catch (...) {
+  return on_exception(c);
 }
 
 int mscan_elide_records(const mscan_mv* recs, uint32_t n, void* out, size_t cap, uint32_t* tile_end16, uint32_t tile_cap,

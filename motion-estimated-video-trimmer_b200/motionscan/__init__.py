@@ -150,6 +150,7 @@ SYMBOLS = {
     "mscan_pack_records": (_i, [_vp, _u64, _vp]),
     "mscan_elide_records": (_i, [_vp, _u32, _vp, C.c_size_t, _vp, _u32, _P(C.c_size_t)]),
     "mscan_elide_bound": (C.c_size_t, [_u32]),
+    "mscan_submit_elided": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _P(_u64)]),
     "mscan_set_staging_mode": (_i, [_vp, _i]),
     "mscan_set_pack_threads": (_i, [_vp, _i]),
     "mscan_reserve_staging": (_i, [_vp]),
@@ -273,6 +274,32 @@ def elide_records(recs: np.ndarray):
     return out[: nbytes.value].copy(), te[:tiles].copy()
 
 
+def elide_frames(recs: np.ndarray, rec_off: np.ndarray, out: np.ndarray | None = None):
+    """mscan_elide_records on every frame of a stream: (enc uint8 array — `out` if given, e.g. a pinned buffer —,
+    enc_off u64[F+1], tile_end16 u32[T])."""
+    n_frames = len(rec_off) - 1
+    parts, ends, enc_off = [], [], np.zeros(n_frames + 1, dtype=np.uint64)
+    at = 0
+    for f in range(n_frames):
+        a, b = int(rec_off[f]), int(rec_off[f + 1])
+        if b > a:
+            e, te = elide_records(np.ascontiguousarray(recs[a:b]))
+            parts.append(e)
+            ends.append(te)
+            at += len(e)
+        enc_off[f + 1] = at
+    if out is None:
+        raw = np.zeros(at + 16, dtype=np.uint8)
+        shift = (-raw.ctypes.data) % 16
+        out = raw[shift : shift + at]
+    assert out.dtype == np.uint8 and len(out) >= at and out.ctypes.data % 16 == 0
+    pos = 0
+    for e in parts:
+        out[pos : pos + len(e)] = e
+        pos += len(e)
+    return out[:at], enc_off, (np.concatenate(ends) if ends else np.zeros(0, np.uint32)).astype(np.uint32)
+
+
 def unelide_records(enc: np.ndarray, tile_end16: np.ndarray, n: int) -> np.ndarray:
     """Reference decoder of the static-elided form (pure numpy): back to MV8_DTYPE records."""
     out = np.zeros(n, dtype=MV8_DTYPE)
@@ -386,6 +413,15 @@ class Context:
         n = len(rec_count)
         first = C.c_uint64()
         self._ck(self.L.mscan_submit_device(self.h, vid, n, _ptr(pts), _ptr(rec_count), d_recs, int(packed), ready_stream or None, C.byref(first)))
+        return first.value
+
+    def submit_elided(self, vid: int, pts, rec_count, enc, enc_off, tile_end16) -> int:
+        """Frames already in the static-elided form (elide_frames): enc uint8 array or address, enc_off u64[F+1]."""
+        n = len(rec_count)
+        first = C.c_uint64()
+        enc_off = np.ascontiguousarray(enc_off, dtype=np.uint64)
+        tile_end16 = np.ascontiguousarray(tile_end16, dtype=np.uint32)
+        self._ck(self.L.mscan_submit_elided(self.h, vid, n, _ptr(pts), _ptr(rec_count), _ptr(enc), _ptr(enc_off), _ptr(tile_end16), C.byref(first)))
         return first.value
 
     def submit_packed_raw(self, vid: int, n_frames: int, pts_ptr: int, cnt_ptr: int, recs_ptr: int):

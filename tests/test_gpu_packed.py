@@ -301,3 +301,49 @@ def test_elided_mode_falls_back_to_mv8_for_cluster_sized_grids():
         st = ctx.stats()
     assert list(counts) == [orc.full_count(cfg, f) for f in frames]
     assert st.records_elided == 0 and st.records_projected == int(cnt.sum())
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_submit_elided_takes_the_callers_own_encoding(pinned):
+    """mscan_submit_elided: frames the caller encoded itself (mscan_elide_records per frame) — DMA'd in place from pinned
+    memory or copied from pageable memory — give the oracle's results; mixed with other layouts in one video."""
+    p = kats.env_params()
+    spec = ms.synth_preset(1, 6)
+    n = 300
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=4)
+    with ms.Context(0, p, 1 << 16, 4 << 20) as ctx:
+        enc, enc_off, te = ms.elide_frames(recs, off)
+        buf = None
+        if pinned:
+            buf = ctx.pinned_array(len(enc) + 16, np.uint8)
+            buf[: len(enc)] = enc
+            enc = buf[: len(enc)]
+        ctx.video_open(1, spec.width, spec.height)
+        # frames [0,100) natively, [100,250) pre-encoded in two calls, the rest projected by the library
+        ctx.set_staging_mode(ms.STAGING_NATIVE)
+        ctx.submit(1, pts[:100], cnt[:100], recs[: int(off[100])])
+        tiles = np.concatenate([[0], np.cumsum((cnt.astype(np.int64) + 1023) // 1024)])
+        for a, b in ((100, 180), (180, 250)):
+            first = ctx.submit_elided(1, pts[a:b], cnt[a:b], enc, enc_off[a : b + 1], te[int(tiles[a]) : int(tiles[b])])
+            assert first == a
+        ctx.set_staging_mode(ms.STAGING_PACK)
+        ctx.submit(1, pts[250:], cnt[250:], recs[int(off[250]) :])
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+        if pinned:
+            ctx.host_fence()
+            ctx.host_free(buf.ctypes.data)
+    assert np.array_equal(flags, of) and np.array_equal(counts, oc)
+    assert st.records_elided == int(off[250] - off[100])
+    # argument checks
+    with ms.Context(0, p, 1 << 12, 1 << 20) as ctx:
+        ctx.video_open(1, spec.width, spec.height)
+        bad_off = enc_off[:3].copy()
+        bad_off[1] += 8
+        with pytest.raises(ms.MscanError) as e:
+            ctx.submit_elided(1, pts[:2], cnt[:2], np.array(enc), bad_off, te)
+        assert e.value.code == ms.ERR_INVALID
+        with pytest.raises(ms.MscanError) as e:
+            ctx.submit_elided(9, pts[:2], cnt[:2], np.array(enc), enc_off[:3], te)
+        assert e.value.code == ms.ERR_INVALID
