@@ -314,6 +314,7 @@ def test_submit_elided_takes_the_callers_own_encoding(pinned):
     of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=4)
     with ms.Context(0, p, 1 << 16, 4 << 20) as ctx:
         enc, enc_off, te = ms.elide_frames(recs, off)
+        enc_pageable = np.array(enc)  # (the pinned copy below is freed before the argument checks)
         buf = None
         if pinned:
             buf = ctx.pinned_array(len(enc) + 16, np.uint8)
@@ -342,8 +343,8 @@ def test_submit_elided_takes_the_callers_own_encoding(pinned):
         bad_off = enc_off[:3].copy()
         bad_off[1] += 8
         with pytest.raises(ms.MscanError) as e:
-            ctx.submit_elided(1, pts[:2], cnt[:2], np.array(enc), bad_off, te)
+            ctx.submit_elided(1, pts[:2], cnt[:2], enc_pageable, bad_off, te)
         assert e.value.code == ms.ERR_INVALID
         with pytest.raises(ms.MscanError) as e:
-            ctx.submit_elided(9, pts[:2], cnt[:2], np.array(enc), enc_off[:3], te)
+            ctx.submit_elided(9, pts[:2], cnt[:2], enc_pageable, enc_off[:3], te)
         assert e.value.code == ms.ERR_INVALID
