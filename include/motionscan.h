@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define MSCAN_ABI_VERSION 2
+#define MSCAN_ABI_VERSION 3 /* 3: mscan_stats grew (records_elided, elided_bytes); submit_device / submit_elided / elide_records / reserve_staging / device_pci_bus_id; MSCAN_STAGING_ELIDE */
 
 /* ---- status codes ------------------------------------------------------ */
 enum {

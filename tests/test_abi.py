@@ -25,7 +25,7 @@ def test_header_symbols_all_exported_and_bound():
     for n in names:
         assert hasattr(L, n), f"{n} declared in motionscan.h but not exported"
         assert n in ms.SYMBOLS, f"{n} has no ctypes prototype"
-    assert L.mscan_abi_version() == 2
+    assert L.mscan_abi_version() == 3
 
 
 def test_struct_layouts():
