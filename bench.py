@@ -37,6 +37,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "motion-estimated-video-trimmer_b200"))
 sys.path.insert(0, str(ROOT / "tests"))
 
+PRODUCER_MODES = ("producers", "producers_elided", "producers_compact")
 METRIC = "mv_records_per_s"
 UNIT = "records/s"
 REC_BYTES = 40
@@ -595,7 +596,11 @@ def run_gpu(args):
     #                   worker pool projects them (bound by reading 40 B/record from DRAM)
     #   packed_pinned   the caller hands over records it projected itself beforehand; only DMA + kernels are timed
     #   elided_pinned   same with the caller's own static-elided encoding (mscan_elide_records → mscan_submit_elided)
-    # `e2e.value` is the best of the modes that start from native host records (the first three).
+    #   compact_pinned  same with the caller's own compaction (mscan_compact_records: moving records only → mscan_submit_packed)
+    # producers runs three times: `producers` with mscan_mv8 on the wire (STAGING_PACK, 8 B/record), `producers_elided` in the
+    # lossless static-elided form (STAGING_ELIDE, ~4.3 B/record) and `producers_compact` as the library does it by default
+    # (STAGING_AUTO: T² > 0 here, so a decode thread's frame travels as its moving records only).
+    # `e2e.value` is the best of the modes that start from native host records (producers*, native_inplace, projected).
     # the same frame count the reference arm derives (sample_frames): both arms scan the same host sample
     e2e_frames = min(sample_frames(args, spec, ms, max(1, len(my_cpus))), n_frames)
     if strong:
@@ -623,6 +628,12 @@ def run_gpu(args):
         h_enc = ctx.pinned_array(z_bound + 16, np.uint8)
         z_enc, z_off, z_te = ms.elide_frames(h_recs, e_off, out=h_enc)
         z_tiles = np.concatenate([[0], np.cumsum((h_cnt.astype(np.int64) + 1023) // 1024)])
+    # compact_pinned: the caller's own compaction of the sample (moving records only) in pinned memory
+    h_cmp = m_cnt = m_off = None
+    if "compact_pinned" in args.e2e_modes.split(","):
+        h_cmp = ctx.pinned_array(e_rec + 8, ms.MV8_DTYPE)
+        _, m_cnt = ms.compact_frames(h_recs, e_off, out=h_cmp)
+        m_off = np.concatenate([[0], np.cumsum(m_cnt.astype(np.int64))])
 
     def tail(vids):
         out = [ctx.collect(v) for v in vids]
@@ -636,7 +647,7 @@ def run_gpu(args):
     def e2e_step(mode):
         for v in e_vids:
             ctx.video_open(v, spec.width, spec.height)
-        if mode in ("producers", "producers_elided"):
+        if mode in PRODUCER_MODES:
             fr, index = ms.feed_run(ctx, e_vids, e_voff, h_pts, h_cnt, e_off, src8, n_threads=n_prod, cpus=my_cpus[:n_prod] if len(my_cpus) >= n_prod else None,
                                     frames_per_submit=args.feed_batch, submit_kind=0)
             t_tail = time.perf_counter()
@@ -657,6 +668,8 @@ def run_gpu(args):
             a, b = int(e_voff[v]), int(e_voff[v + 1])
             if mode == "elided_pinned":
                 ctx.submit_elided(v, h_pts[a:b], h_cnt[a:b], h_enc, z_off[a : b + 1], z_te[int(z_tiles[a]) : int(z_tiles[b])])
+            elif mode == "compact_pinned":
+                ctx.submit_packed_raw(v, b - a, h_pts.ctypes.data + 8 * a, m_cnt.ctypes.data + 4 * a, h_cmp.ctypes.data + 8 * int(m_off[a]))
             elif mode == "packed_pinned":
                 ctx.submit_packed_raw(v, b - a, h_pts.ctypes.data + 8 * a, h_cnt.ctypes.data + 4 * a, h_r8.ctypes.data + 8 * int(e_off[a]))
             else:
@@ -666,12 +679,13 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     modes = {}
     seg_ref = None
-    all_modes = ("producers", "producers_elided", "native_inplace", "projected", "packed_pinned", "elided_pinned")
+    all_modes = ("producers", "producers_elided", "producers_compact", "native_inplace", "projected", "packed_pinned", "elided_pinned",
+                 "compact_pinned")
     run_modes = [m for m in all_modes if m in args.e2e_modes.split(",")] or list(all_modes)
     for mode in run_modes:
-        # producers: mscan_mv8 on the wire (STAGING_PACK); producers_elided: the library's default for a decode thread's
-        # pageable frame (STAGING_AUTO → static-elided form)
-        ctx.set_staging_mode({"projected": ms.STAGING_PACK, "producers": ms.STAGING_PACK}.get(mode, ms.STAGING_AUTO))
+        # producers: mscan_mv8 on the wire (STAGING_PACK); producers_elided: the lossless static-elided form (STAGING_ELIDE);
+        # producers_compact: the library's default for a decode thread's pageable frame (STAGING_AUTO → moving records only)
+        ctx.set_staging_mode({"projected": ms.STAGING_PACK, "producers": ms.STAGING_PACK, "producers_elided": ms.STAGING_ELIDE}.get(mode, ms.STAGING_AUTO))
         for _ in range(2):
             e2e_out = e2e_step(mode)
         ctx.sync()
@@ -696,13 +710,13 @@ def run_gpu(args):
             # the host-fed results must equal the device-resident ones for the same frames, and every mode's segments agree
             "matches_device_resident": bool(np.array_equal(e_flags, flags[:e2e_frames])) and seg_bytes == seg_ref,
         }
-        if mode in ("projected", "producers", "producers_elided"):
+        if mode == "projected" or mode in PRODUCER_MODES:
             modes[mode]["host_threads"] = pack_threads if mode == "projected" else n_prod
             modes[mode]["project_cpu_ms_per_step"] = est.project_ms / e2e_steps
             modes[mode]["records_projected_per_step"] = int(est.records_projected // e2e_steps)
-        if mode == "producers_elided":
+        if mode in ("producers_elided", "producers_compact"):
             modes[mode]["wire_bytes_per_record"] = est.elided_bytes / max(est.records_elided, 1)
-        if mode in ("producers", "producers_elided"):
+        if mode in PRODUCER_MODES:
             fs = np.array(feed_stats)
             wall, hot_max, hot_sum, sd_max, sd_sum, t_tail, submits = fs.sum(axis=0)
             # the reference arm's protocol on this arm: records / (slowest producer's time inside mscan_submit + the tail)
@@ -726,7 +740,7 @@ def run_gpu(args):
     # can carry, so it is capped by the rate measured in this same run with the link saturated (packed_pinned: the same
     # records already projected, DMA + K-A + tail by wall clock). Both terms and the plain wall-clock figure of the
     # producers run (stand-in included) are in the line.
-    for name in ("producers", "producers_elided"):
+    for name in PRODUCER_MODES:
         if name not in modes:
             continue
         pm = modes[name]
@@ -736,16 +750,20 @@ def run_gpu(args):
             cap = modes["elided_pinned"]["value"]
             cap_how = ("the rate measured in this run with the link saturated in the same wire form (elided_pinned: the caller's own "
                        "static-elided encoding in pinned memory, DMA + K-A + tail by wall clock)")
-        elif name == "producers_elided":  # fewer bytes per record on the same link: the measured link-bound rate scales with the wire size
+        elif name == "producers_compact" and "compact_pinned" in modes:
+            cap = modes["compact_pinned"]["value"]
+            cap_how = ("the rate measured in this run with the caller's own compaction of the same sample in pinned memory (compact_pinned: "
+                       "only the moving records cross the link; DMA + K-A + tail by wall clock — the tail dominates it)")
+        elif name != "producers":  # fewer bytes per record on the same link: the measured link-bound rate scales with the wire size
             cap = cap * 8.0 / max(pm["wire_bytes_per_record"], 1e-9)
-            cap_how += f", scaled by 8 / {pm['wire_bytes_per_record']:.2f} B per record measured on the wire in the static-elided form"
+            cap_how += f", scaled by 8 / {pm['wire_bytes_per_record']:.2f} B per record measured on the wire in this form"
         pm["value_wall_incl_decode_standin"] = pm["value"]
         pm["link_bound_value"] = cap
         pm["value"] = min(pm["hot_path_only_value"], cap)
         pm["value_how"] = ("min(hot_path_only_value, link_bound_value): records / (slowest decode thread's time inside mscan_submit + tail), "
                            "capped by " + cap_how + "; value_wall_incl_decode_standin is the same run by wall clock with the decode "
                            "stand-in's own work (writing 40 B/record into the side-data buffer) included")
-    e2e_mode = max([m for m in ("producers", "producers_elided", "native_inplace", "projected") if m in modes] or list(modes),
+    e2e_mode = max([m for m in PRODUCER_MODES + ("native_inplace", "projected") if m in modes] or list(modes),
                    key=lambda m: modes[m]["value"])
     best = modes[e2e_mode]
     e2e_value, e2e_launches, e2e_ok = best["value"], best["launches"], all(m["matches_device_resident"] for m in modes.values())
@@ -871,8 +889,10 @@ def run_gpu(args):
                 "modes": modes,
                 "value_wall_incl_decode_standin": best.get("value_wall_incl_decode_standin"),
                 "how": "per step: mscan_video_open, the mode's submits of native 40-B host records, collect, segments_batch, close; max over "
-                "ranks; value = best of producers / producers_elided (decode-worker stand-ins submitting cache-hot frames per frame, concurrently; "
-                "8 B/record over PCIe, or ~4.3 B/record in the static-elided form; timed like the reference arm — see modes.*.value_how), native_inplace (pinned records DMA'd in place, 40 B/record, "
+                "ranks; value = best of producers / producers_elided / producers_compact (decode-worker stand-ins submitting cache-hot frames per "
+                "frame, concurrently; 8 B/record over PCIe, ~4.3 B/record in the lossless static-elided form, or — the library's default while "
+                "MV_THRESHOLD_SQ > 0 — only the moving records, since a record with src == dst cannot pass motion_scanner.cpp:251; timed like the "
+                "reference arm — see modes.*.value_how), native_inplace (pinned records DMA'd in place, 40 B/record, "
                 "wall clock) and projected (whole videos from host DRAM through the library's pool, wall clock); packed_pinned "
                 "(caller-projected records) is reported in modes only. When a mode flattens with more GPUs the saturated resource is the "
                 "host (its cores and DRAM): link_limit_records_per_s is what the measured PCIe links could carry at 8 B/record",
@@ -895,6 +915,8 @@ def run_gpu(args):
     ctx.host_free(h_recs.ctypes.data)
     if h_enc is not None:
         ctx.host_free(h_enc.ctypes.data)
+    if h_cmp is not None:
+        ctx.host_free(h_cmp.ctypes.data)
     ctx.host_free(h_r8.ctypes.data)
     ctx.host_free(h_pts.ctypes.data)
     ctx.close()
@@ -915,7 +937,7 @@ def main():
     ap.add_argument("--e2e-records", type=float, default=6e7, help="records of the host-resident sample both arms scan (~2.4 GB pinned)")
     ap.add_argument("--e2e-frames", type=int, default=0, help="override: frames of the host sample")
     ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--e2e-modes", default="producers,producers_elided,native_inplace,projected,packed_pinned,elided_pinned", help="experiments: subset of the e2e modes to run")
+    ap.add_argument("--e2e-modes", default="producers,producers_elided,producers_compact,native_inplace,projected,packed_pinned,elided_pinned,compact_pinned", help="experiments: subset of the e2e modes to run")
     ap.add_argument("--feed-batch", type=int, default=1, help="frames per mscan_submit of the producer stand-ins (1 = per frame, like check_frame)")
     ap.add_argument("--feed-threads", type=int, default=0, help="producer stand-in threads per rank (0 = one per CPU of the rank)")
     ap.add_argument("--ref-repeats", type=int, default=5, help="--impl reference: independent runs (value = median)")

@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define MSCAN_ABI_VERSION 3 /* 3: mscan_stats grew (records_elided, elided_bytes); submit_device / submit_elided / elide_records / reserve_staging / device_pci_bus_id; MSCAN_STAGING_ELIDE */
+#define MSCAN_ABI_VERSION 3 /* 3: mscan_stats grew (records_elided, elided_bytes); submit_device / submit_elided / elide_records / compact_records / reserve_staging / device_pci_bus_id; MSCAN_STAGING_ELIDE / _COMPACT */
 
 /* ---- status codes ------------------------------------------------------ */
 enum {
@@ -91,15 +91,23 @@ typedef struct mscan_mv8 {
 enum {
   MSCAN_STAGING_AUTO = 0,  /* pinned source: DMA the native records in place (no host pass);
                               pageable source: the staging pass keeps the 8 bytes the path reads — as mscan_mv8,
-                              projected by the worker pool, for submits above 256 Ki records; in the static-elided
-                              form (see MSCAN_STAGING_ELIDE), encoded by the calling thread, below (default)   */
+                              projected by the worker pool, for submits above 256 Ki records; below that (a decode
+                              thread handing over its own frames) the calling thread leaves static macroblocks out:
+                              MSCAN_STAGING_COMPACT while MV_THRESHOLD_SQ > 0, MSCAN_STAGING_ELIDE otherwise (default) */
   MSCAN_STAGING_PACK = 1,  /* always project on the host, even from pinned memory                */
   MSCAN_STAGING_NATIVE = 2, /* never project: pageable sources are memcpy'd as 40-byte records   */
-  MSCAN_STAGING_ELIDE = 3   /* project, and send static macroblocks (src == dst, ~90 % of a CCTV stream) as their 4 dst
+  MSCAN_STAGING_ELIDE = 3,  /* project, and send static macroblocks (src == dst, ~90 % of a CCTV stream) as their 4 dst
                                bytes + a mask bit: a lossless transport form of the mscan_mv8 sequence that the kernel
                                expands again (≈ 4.6 B/record over PCIe at 10 % moving records). The calling thread does
                                the encoding — made for decode threads submitting their own frames. Grids beyond one
                                CTA's shared memory (8K and larger) are sent as mscan_mv8 instead. */
+  MSCAN_STAGING_COMPACT = 4 /* send the mscan_mv8 projections of the MOVING records only (src != dst), nothing for a static
+                               macroblock: with MV_THRESHOLD_SQ > 0 a record whose src equals its dst has mag_sq == 0 and
+                               leaves check_frame at src/motion_scanner.cpp:251 before it can vote, so flags and cluster
+                               counts do not depend on it (≈ 0.2–0.8 B/record over PCIe at 2–10 % moving records). The
+                               calling thread compacts; the only operation on the data is that byte equality — every
+                               record that could pass :251 reaches the kernel unchanged. Contexts whose threshold is
+                               zero, negative or NaN (static records vote there) use MSCAN_STAGING_ELIDE instead. */
 };
 
 /* ---- TimeSegment (include/motion_trim/types.hpp:56-59) ----------------- */
@@ -156,8 +164,8 @@ typedef struct mscan_stats {
   uint64_t records_projected; /* native records the staging pass projected to mscan_mv8  */
   double project_ms;          /* host wall time spent in that projection                 */
   uint64_t peer_bytes;        /* bytes mscan_video_append_from copied in from other contexts */
-  uint64_t records_elided;    /* records sent in the static-elided form (MSCAN_STAGING_ELIDE)   */
-  uint64_t elided_bytes;      /* … and the bytes they took                                      */
+  uint64_t records_elided;    /* native records that went through MSCAN_STAGING_ELIDE / _COMPACT */
+  uint64_t elided_bytes;      /* … and the record bytes that were sent for them                  */
 } mscan_stats;
 
 typedef struct mscan_ctx mscan_ctx;
@@ -229,6 +237,11 @@ int mscan_submit_device(mscan_ctx* ctx, uint32_t video_id, uint32_t n_frames, co
 /* The projection itself, usable from any thread without a context or a GPU: out[i] = bytes 6..13 of
  * recs[i]. out must be 8-byte aligned; written with streaming stores (it is read next by the DMA engine). */
 int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out);
+/* The compaction of MSCAN_STAGING_COMPACT, usable from any thread without a context or a GPU: out receives the
+ * projections of the records with src != dst, in order, *n_out how many. out: 8-byte aligned, room for n records. A
+ * caller that compacts into pinned memory hands the result to mscan_submit_packed with the per-frame MOVING counts as
+ * rec_count — only valid for contexts with MV_THRESHOLD_SQ > 0 (see MSCAN_STAGING_COMPACT). */
+int mscan_compact_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out, uint64_t* n_out);
 /* The static-elided transport form itself (what MSCAN_STAGING_ELIDE puts on the wire), usable without a context or a
  * GPU — ONE frame of n native records. The frame is cut into tiles of 1024 records (the last one shorter), tiles follow
  * each other 16-byte aligned; a tile is

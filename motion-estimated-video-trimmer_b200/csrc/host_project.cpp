@@ -1,5 +1,6 @@
-// host_project.cpp — the host projection AVMotionVector → mscan_mv8 used by the staging pass of mscan_submit and
-// by mscan_pack_records (compiled by g++, not nvcc: it carries AVX-512 code paths chosen at run time).
+// host_project.cpp — the host passes over native records: the projection AVMotionVector → mscan_mv8 used by the staging
+// pass of mscan_submit and by mscan_pack_records, the static-elided form and the moving-record compaction (compiled by
+// g++, not nvcc: it carries AVX-512 code paths chosen at run time).
 //
 // Bytes 6..13 of a native 40-byte record are src_x, src_y, dst_x, dst_y — the only fields the path reads
 // (reference src/motion_scanner.cpp:243-256) — and they are contiguous: the projection is a pure byte selection,
@@ -304,6 +305,74 @@ uint64_t mvz_encode_frame(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t*
   return at;
 }
 
+// ---- moving-record compaction ----------------------------------------------------------------------------------
+// What MSCAN_STAGING_COMPACT puts on the wire: the mscan_mv8 projections of the records whose src differs from their
+// dst, in record order — nothing at all for a static macroblock. Valid while the threshold is positive: a record with
+// src == dst has mag_sq == 0 (src/motion_scanner.cpp:246-248) and `0 < T²` sends it to `continue` at :251 before it
+// can vote, so the frame's flag and cluster count do not depend on it. The only operation on the data is the byte
+// equality of the two halves of the projection; every record that could pass :251 reaches the kernel unchanged.
+// out needs room for n records; returns the number written.
+namespace {
+
+uint64_t compact_scalar(const uint8_t* in, uint64_t n, uint64_t* out) {
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t v;
+    memcpy(&v, in + (size_t)kRec * i + 6, sizeof v);
+    out[m] = v;
+    m += (uint32_t)v != (uint32_t)(v >> 32);
+  }
+  return m;
+}
+
+#if defined(__x86_64__)
+// 8 records per step: the projection's byte gather, then "halves differ" as one qword compare and one compress.
+// The cost of the pass when the frame is cache-hot is its loads, and a 64-byte load that straddles two lines costs
+// two: since 40 k ≡ -a (mod 64) has a solution k < 8 for every 8-byte aligned a, the first k records go through the
+// portable loop and every block after them starts on a line (tools/exp_gather.cpp: 0.55 against 0.8 ns/record).
+__attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) uint64_t compact_vbmi(const uint8_t* in, uint64_t n, uint64_t* out) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(in);
+  if (a & 7u) return compact_scalar(in, n, out);  // (AVMotionVector holds a uint64: never the case for real side data)
+  uint64_t head = ((((64 - (a & 63)) & 63) >> 3) * 5) & 7;  // k with 40 k ≡ -a (mod 64): 5 is its own inverse mod 8
+  if (head > n) head = n;
+  uint64_t m = compact_scalar(in, head, out);
+  in += (size_t)kRec * head;
+  n -= head;
+  const Tables& t = tables();
+  const __m512i ia = _mm512_load_si512(t.a), ib = _mm512_load_si512(t.b), ic = _mm512_load_si512(t.c);
+  const __mmask64 mb = t.mask_b, mc = t.mask_c;
+  const uint64_t blocks = n / 8;
+  for (uint64_t g = 0; g < blocks; ++g) {
+    const uint8_t* p = in + 320 * g;
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 64), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 128), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 192), _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 256), _MM_HINT_T0);
+    const __m512i z0 = _mm512_load_si512(p), z1 = _mm512_load_si512(p + 64), z2 = _mm512_load_si512(p + 128),
+                  z3 = _mm512_load_si512(p + 192), z4 = _mm512_load_si512(p + 256);
+    __m512i v = _mm512_permutex2var_epi8(z0, ia, z1);
+    v = _mm512_mask_mov_epi8(v, mb, _mm512_permutex2var_epi8(z2, ib, z3));
+    v = _mm512_mask_permutexvar_epi8(v, mc, ic, z4);  // 8 records: src | dst << 32
+    const __mmask8 k = _mm512_cmpneq_epi64_mask(v, _mm512_rol_epi64(v, 32));  // halves differ ⇔ moving
+    if (k) {
+      _mm512_storeu_si512(out + m, _mm512_maskz_compress_epi64(k, v));  // (a whole register: at most 8 g records precede it, so it ends inside out[n))
+      m += (uint64_t)__builtin_popcount((unsigned)k);
+    }
+  }
+  return m + compact_scalar(in + 320 * blocks, n - 8 * blocks, out + m);
+}
+#endif
+
+}  // namespace
+
+uint64_t compact_moving(const uint8_t* in, uint64_t n, uint64_t* out) {
+#if defined(__x86_64__)
+  if (have_vbmi() && n >= 16) return compact_vbmi(in, n, out);
+#endif
+  return compact_scalar(in, n, out);
+}
+
 #if defined(__x86_64__)
 namespace {
 __attribute__((target("avx512f"))) uint64_t stream_copy_512(const uint8_t* from, uint8_t* to, uint64_t bytes) {
@@ -318,8 +387,14 @@ __attribute__((target("avx512f"))) uint64_t stream_copy_512(const uint8_t* from,
 // DMA engine, not by this core
 void stream_copy(const uint8_t* from, uint8_t* to, uint64_t bytes) {
 #if defined(__x86_64__)
-  if (!plain_stores() && (reinterpret_cast<uintptr_t>(to) & 15u) == 0) {
+  if (!plain_stores() && (reinterpret_cast<uintptr_t>(to) & 7u) == 0) {
     uint64_t i = 0;
+    if ((reinterpret_cast<uintptr_t>(to) & 15u) && bytes >= 8) {  // mscan_mv8 offsets are multiples of 8
+      long long v;
+      memcpy(&v, from, sizeof v);
+      _mm_stream_si64(reinterpret_cast<long long*>(to), v);
+      i = 8;
+    }
     for (; i + 16 <= bytes && ((reinterpret_cast<uintptr_t>(to + i)) & 63u); i += 16)  // up to the first full line
       _mm_stream_si128(reinterpret_cast<__m128i*>(to + i), _mm_loadu_si128(reinterpret_cast<const __m128i*>(from + i)));
     if (have_vbmi()) i += stream_copy_512(from + i, to + i, bytes - i);

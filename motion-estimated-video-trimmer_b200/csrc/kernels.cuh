@@ -105,6 +105,8 @@ uint64_t mvz_bound(uint64_t n_recs, uint64_t n_frames);  // bytes the encoding o
 // from `out`; returns the bytes written (a multiple of 16)
 uint64_t mvz_encode_frame(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t* tile_end16);
 void stream_copy(const uint8_t* from, uint8_t* to, uint64_t bytes);
+// mscan_mv8 projections of the records with src != dst, in order (host_project.cpp); out: room for n records + 64 bytes
+uint64_t compact_moving(const uint8_t* in, uint64_t n, uint64_t* out);
 
 // ---- aux: exclusive scan of per-frame record counts, synthetic stream generation
 cudaError_t offsets_launch(const uint32_t* counts, uint32_t n, uint64_t* off, uint64_t* block_scratch,

@@ -374,7 +374,7 @@ struct mscan_ctx {
   std::vector<SegJob> dev_jobs_cached;
 
   // host projection (see project_records)
-  int staging_mode = MSCAN_STAGING_AUTO;
+  std::atomic<int> staging_mode{MSCAN_STAGING_AUTO};  // (read before the mutex is taken by the per-frame fast path)
   int pack_threads = 0;  // threads of the shared pool one large submit of this context may use; 0 → all
   uint32_t win_shift = 21;  // log2 of the H2D copy window (2 MiB: 38 µs on a Gen5 x16 link against ~3 µs to enqueue a copy)
   // counters written outside `mu` (folded into `stats` by mscan_get_stats)
@@ -1321,7 +1321,7 @@ static int fill_and_commit(mscan_ctx* c, Slab& s, FillKind kind, uint64_t off, u
                               std::memory_order_relaxed);
     c->a_records_projected.fetch_add(n_recs, std::memory_order_relaxed);
   } else if (kind == kFillMemcpy) {
-    std::memcpy(s.h_recs + off, from, nbytes);
+    stream_copy(from, s.h_recs + off, nbytes);  // (the ring is read next by the DMA engine, not by this core)
   } else if (kind == kFillInPlace) {
     std::lock_guard<std::mutex> issue(c->issue_mu);
     cudaError_t e = use_device(c);
@@ -1553,9 +1553,73 @@ static int submit_elide(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, cons
   return MSCAN_OK;
 }
 
+// A submit call that hands its frames over in several pieces (submit_compact): the video-local index range of the WHOLE
+// call is reserved by the piece that is placed first — in the same critical section as its first frames, so that
+// per-frame submits from many decode threads keep video order == log order — and the later pieces place into it.
+struct CallSpan {
+  uint32_t total_frames;  // frames of the whole call
+  uint32_t f0;            // index, in the call, of this piece's first frame
+  uint64_t vbase;         // set by the first piece
+  bool have;
+  // what the piece's host pass did: added to the context's counters inside the piece's own critical section (four
+  // shared atomics per frame from every decode thread would cost more than the bookkeeping they count)
+  uint64_t st_records = 0, st_wire_bytes = 0, st_ns = 0;
+};
+
+static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                       const void* recs, bool src_packed, uint64_t* first_frame_out, CallSpan* span);
+
+// mscan_submit under MSCAN_STAGING_COMPACT (and AUTO for a decode thread's own frame while the threshold is positive):
+// the calling thread writes the projections of the MOVING records of its frames into a private scratch, piece by piece,
+// and each piece goes through the packed submit (pageable mscan_mv8 → streaming copy into the pinned ring). A frame's
+// record count on the GPU side is its number of moving records; results are unchanged because a static record cannot
+// pass motion_scanner.cpp:251 while T² > 0 (host_project.cpp, compact_moving). The caller has released the mutex.
+static int submit_compact(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
+                          const uint8_t* src, uint64_t* first_frame_out) {
+  thread_local std::vector<uint64_t> scratch;    // one piece: mscan_mv8 of its moving records
+  thread_local std::vector<uint32_t> moving;     // per frame of the piece: how many
+  CallSpan span{n_frames, 0, 0, false};
+  uint32_t f = 0;
+  uint64_t src_rec = 0;
+  while (f < n_frames) {
+    uint32_t g = f;
+    uint64_t piece_recs = 0;
+    while (g < n_frames && (g == f || piece_recs + rec_count[g] <= kPoolMinRecs)) piece_recs += rec_count[g++];
+    const uint32_t nf = g - f;
+    if (piece_recs && !src) {
+      if (span.have) {  // give the unplaced rest of the reserved range back (like submit_impl's own rollback)
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->videos.find(video_id);
+        if (it != c->videos.end() && it->second.n_frames == span.vbase + n_frames) it->second.n_frames = span.vbase + f;
+      }
+      return fail(c, MSCAN_ERR_INVALID, "null recs with non-zero rec_count");
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    scratch.resize((size_t)piece_recs + 8);
+    moving.resize(nf);
+    uint64_t at = 0, done = 0;
+    for (uint32_t i = 0; i < nf; ++i) {
+      const uint32_t n = rec_count[f + i];
+      const uint64_t m = n ? compact_moving(src + (size_t)kRecBytes * (src_rec + done), n, scratch.data() + at) : 0;
+      moving[i] = (uint32_t)m;
+      at += m;
+      done += n;
+    }
+    span.st_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    span.st_records = piece_recs;
+    span.st_wire_bytes = 8 * at;
+    span.f0 = f;
+    int rc = submit_impl(c, video_id, nf, pts + f, moving.data(), scratch.data(), true, f == 0 ? first_frame_out : nullptr, &span);
+    if (rc) return rc;
+    f = g;
+    src_rec += piece_recs;
+  }
+  return MSCAN_OK;
+}
+
 // Shared body of mscan_submit (native 40-byte records) and mscan_submit_packed (mscan_mv8).
 static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
-                       const void* recs, bool src_packed, uint64_t* first_frame_out) try {
+                       const void* recs, bool src_packed, uint64_t* first_frame_out, CallSpan* span) try {
   ApiTimer trace_(c, "mscan_submit[_packed]");
   if (!c) return MSCAN_ERR_INVALID;
   if (n_frames == 0) {
@@ -1580,6 +1644,14 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
       if (!pinned && src_bytes >= kAttrQueryBytes) pinned = is_pinned(recs);
     }
   }
+  // Static macroblocks (src == dst) are not sent as 8 bytes. While the threshold is positive they cannot vote and the
+  // calling thread sends the moving records only (MSCAN_STAGING_COMPACT; decided without the mutex: the pieces take it
+  // themselves); otherwise they go as their 4 dst bytes (mvz, MSCAN_STAGING_ELIDE — the cluster kernel reads native and
+  // mv8 records only).
+  const int mode = c->staging_mode.load(std::memory_order_relaxed);
+  const bool small_auto = mode == MSCAN_STAGING_AUTO && !pinned && total <= kPoolMinRecs;
+  if (!src_packed && !span && (mode == MSCAN_STAGING_COMPACT || small_auto) && c->ithr > 0)
+    return submit_compact(c, video_id, n_frames, pts, rec_count, src, first_frame_out);
   std::unique_lock<std::mutex> lk(c->mu, std::defer_lock);
   lock_briefly(lk);
   auto it = c->videos.find(video_id);
@@ -1588,13 +1660,27 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   // cluster kernel (grids beyond one CTA's shared memory) reads native and mv8 records only
   // (also what AUTO does with a pageable submit small enough that the caller projects alone — a decode thread handing
   // over its own frame: the encoding costs about what the projection costs and nearly halves the bytes on the link)
-  const bool elide = c->staging_mode == MSCAN_STAGING_ELIDE || (c->staging_mode == MSCAN_STAGING_AUTO && !pinned && total <= kPoolMinRecs);
+  const bool elide = mode == MSCAN_STAGING_ELIDE || mode == MSCAN_STAGING_COMPACT || small_auto;
   if (!src_packed && elide && !c->plan_packed.cluster && !c->plan_packed.global_cnt) {
     lk.unlock();
     return submit_elide(c, video_id, n_frames, pts, rec_count, src, first_frame_out);
   }
-  const uint64_t vbase = it->second.n_frames;  // this call owns video-local indices [vbase, vbase + n_frames)
-  it->second.n_frames += n_frames;
+  // this call owns video-local indices [vbase, vbase + n_frames) (a piece of a larger call: its part of that call's range)
+  CallSpan own{n_frames, 0, 0, false};
+  if (!span) span = &own;
+  if (!span->have) {
+    span->vbase = it->second.n_frames;
+    it->second.n_frames += span->total_frames;
+    span->have = true;
+  }
+  if (span->st_records) {
+    c->stats.records_projected += span->st_records;
+    c->stats.records_elided += span->st_records;
+    c->stats.elided_bytes += span->st_wire_bytes;
+    c->stats.project_ms += (double)span->st_ns * 1e-6;
+    span->st_records = 0;
+  }
+  const uint64_t vbase = span->vbase + span->f0;
   if (first_frame_out) *first_frame_out = vbase;
   // on failure the indices not yet backed by log frames are given back (when no later call has reserved behind them)
   struct Rollback {
@@ -1602,13 +1688,14 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     std::unique_lock<std::mutex>& lk;
     uint32_t video_id, n_frames;
     const uint32_t& f;
-    uint64_t vbase;
+    uint64_t vbase;       // of this piece
+    uint64_t call_end;    // end of the whole call's reserved range
     bool armed = true;
     ~Rollback() {
       if (!armed || f >= n_frames) return;
       if (!lk.owns_lock()) lk.lock();
       auto it = c->videos.find(video_id);
-      if (it != c->videos.end() && it->second.n_frames == vbase + n_frames) it->second.n_frames = vbase + f;
+      if (it != c->videos.end() && it->second.n_frames == call_end) it->second.n_frames = vbase + f;
     }
   };
   // How the records reach the slab: native+pinned → DMA in place (40 B/record over PCIe, no host work);
@@ -1616,8 +1703,8 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   // packed → as is (DMA in place when pinned, memcpy into staging otherwise).
   bool project = false;
   if (!src_packed) {
-    if (c->staging_mode == MSCAN_STAGING_PACK || c->staging_mode == MSCAN_STAGING_ELIDE) project = true;
-    else if (c->staging_mode == MSCAN_STAGING_NATIVE) project = false;
+    if (mode == MSCAN_STAGING_PACK || mode == MSCAN_STAGING_ELIDE || mode == MSCAN_STAGING_COMPACT) project = true;
+    else if (mode == MSCAN_STAGING_NATIVE) project = false;
     else project = !pinned;
   }
   const uint8_t slab_fmt = (src_packed || project) ? (uint8_t)kLayoutMv8 : (uint8_t)kLayoutNative;
@@ -1634,7 +1721,7 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
   uint32_t f = 0;
   uint64_t src_rec = 0;
   int result = MSCAN_OK;
-  Rollback rollback{c, lk, video_id, n_frames, f, vbase};
+  Rollback rollback{c, lk, video_id, n_frames, f, vbase, span->vbase + span->total_frames};
   while (f < n_frames) {
     // (re)validate the video: the mutex was released while the previous piece was being filled
     it = c->videos.find(video_id);
@@ -1743,13 +1830,13 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
 
 int mscan_submit(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
                  const mscan_mv* recs, uint64_t* first_frame_out) {
-  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, false, first_frame_out);
+  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, false, first_frame_out, nullptr);
 }
 
 int mscan_submit_packed(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
                         const mscan_mv8* recs, uint64_t* first_frame_out) {
   if (recs && (reinterpret_cast<uintptr_t>(recs) & 7u)) return fail(c, MSCAN_ERR_INVALID, "packed records must be 8-byte aligned");
-  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, true, first_frame_out);
+  return submit_impl(c, video_id, n_frames, pts, rec_count, recs, true, first_frame_out, nullptr);
 }
 
 // Frames whose records already lie in this GPU's memory: appended to the video's frame log like a host submit and
@@ -1860,6 +1947,13 @@ int mscan_pack_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out) {
   return MSCAN_OK;
 }
 
+int mscan_compact_records(const mscan_mv* recs, uint64_t n, mscan_mv8* out, uint64_t* n_out) {
+  if ((n && (!recs || !out)) || !n_out) return MSCAN_ERR_INVALID;
+  if (reinterpret_cast<uintptr_t>(out) & 7u) return MSCAN_ERR_INVALID;
+  *n_out = n ? compact_moving(reinterpret_cast<const uint8_t*>(recs), n, reinterpret_cast<uint64_t*>(out)) : 0;
+  return MSCAN_OK;
+}
+
 int mscan_submit_elided(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const double* pts, const uint32_t* rec_count,
                         const void* enc, const uint64_t* enc_off, const uint32_t* tile_end16, uint64_t* first_frame_out) try {
   ApiTimer trace_(c, "mscan_submit_elided");
@@ -1933,10 +2027,11 @@ size_t mscan_elide_bound(uint32_t n) { return (size_t)mvz_bound(n, 1); }
 
 int mscan_set_staging_mode(mscan_ctx* c, int mode) {
   if (!c) return MSCAN_ERR_INVALID;
-  if (mode != MSCAN_STAGING_AUTO && mode != MSCAN_STAGING_PACK && mode != MSCAN_STAGING_NATIVE && mode != MSCAN_STAGING_ELIDE)
+  if (mode != MSCAN_STAGING_AUTO && mode != MSCAN_STAGING_PACK && mode != MSCAN_STAGING_NATIVE && mode != MSCAN_STAGING_ELIDE &&
+      mode != MSCAN_STAGING_COMPACT)
     return fail(c, MSCAN_ERR_INVALID, "unknown staging mode %d", mode);
   std::lock_guard<std::mutex> lk(c->mu);
-  c->staging_mode = mode;
+  c->staging_mode.store(mode, std::memory_order_relaxed);
   return MSCAN_OK;
 }
 

@@ -32,7 +32,7 @@ MV_DTYPE = np.dtype(
 # mscan_mv8: bytes 6..13 of the native record
 MV8_DTYPE = np.dtype([("src_x", "<i2"), ("src_y", "<i2"), ("dst_x", "<i2"), ("dst_y", "<i2")])
 SEG_DTYPE = np.dtype([("start", "<f8"), ("end", "<f8")])
-STAGING_AUTO, STAGING_PACK, STAGING_NATIVE, STAGING_ELIDE = 0, 1, 2, 3
+STAGING_AUTO, STAGING_PACK, STAGING_NATIVE, STAGING_ELIDE, STAGING_COMPACT = 0, 1, 2, 3, 4
 
 
 class Params(C.Structure):
@@ -148,6 +148,7 @@ SYMBOLS = {
     "mscan_submit_device": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _i, _vp, _P(_u64)]),
     "mscan_device_pci_bus_id": (_i, [_i, C.c_char_p, _i]),
     "mscan_pack_records": (_i, [_vp, _u64, _vp]),
+    "mscan_compact_records": (_i, [_vp, _u64, _vp, _P(_u64)]),
     "mscan_elide_records": (_i, [_vp, _u32, _vp, C.c_size_t, _vp, _u32, _P(C.c_size_t)]),
     "mscan_elide_bound": (C.c_size_t, [_u32]),
     "mscan_submit_elided": (_i, [_vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _P(_u64)]),
@@ -255,6 +256,41 @@ def pack_records(recs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
     if rc:
         raise MscanError(rc, "mscan_pack_records")
     return out
+
+
+def compact_records(recs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+    """mscan_compact_records: the 8-byte projections of the records with src != dst, in order (the wire form of
+    STAGING_COMPACT). Returns the filled prefix of `out` (e.g. a pinned buffer with room for len(recs) records)."""
+    assert recs.dtype == MV_DTYPE and recs.flags["C_CONTIGUOUS"]
+    if out is None:
+        out = np.empty(max(len(recs), 1), dtype=MV8_DTYPE)
+    assert out.dtype == MV8_DTYPE and len(out) >= len(recs)
+    n = _u64(0)
+    rc = lib().mscan_compact_records(_ptr(recs) if len(recs) else None, len(recs), _ptr(out), C.byref(n))
+    if rc:
+        raise MscanError(rc, "mscan_compact_records")
+    return out[: n.value]
+
+
+def compact_frames(recs: np.ndarray, off: np.ndarray, out: np.ndarray | None = None):
+    """compact_records on every frame of a stream: (mv8 records of the moving records back to back — the filled prefix
+    of `out` if given —, per-frame moving counts as uint32)."""
+    n_frames = len(off) - 1
+    if out is None:
+        out = np.empty(max(int(off[-1] - off[0]), 1), dtype=MV8_DTYPE)
+    cnt = np.zeros(n_frames, np.uint32)
+    at = 0
+    L = lib()
+    n = _u64(0)
+    for f in range(n_frames):
+        a, b = int(off[f]), int(off[f + 1])
+        if b > a:
+            rc = L.mscan_compact_records(recs.ctypes.data + 40 * a, b - a, out.ctypes.data + 8 * at, C.byref(n))
+            if rc:
+                raise MscanError(rc, "mscan_compact_records")
+            cnt[f] = n.value
+            at += n.value
+    return out[:at], cnt
 
 
 def elide_records(recs: np.ndarray):

@@ -191,3 +191,80 @@ def test_elided_form_round_trips_on_cpu():
             assert len(enc) <= 8 * n + 352 * max(len(te), 1)
     enc, _ = ms.elide_records(static)
     assert len(enc) / len(static) < 4.4  # 4 B dst + 8 B header per 32 records
+
+
+def _moving_mv8(recs):
+    r8 = ms.pack_records(recs) if len(recs) else np.zeros(0, ms.MV8_DTYPE)
+    keep = (r8["src_x"] != r8["dst_x"]) | (r8["src_y"] != r8["dst_y"])
+    return r8[keep]
+
+
+def test_compaction_keeps_exactly_the_moving_records_in_order():
+    """mscan_compact_records (the wire form of MSCAN_STAGING_COMPACT): the projections of the records with src != dst,
+    in record order — at every length around the 8-record vector step, for static, mixed and all-moving input."""
+    from test_oracle_kats import random_frame
+
+    rng = np.random.default_rng(11)
+    cnt, off, recs, pts = ms.synth_host(ms.synth_preset(4, 5), 1, 2)
+    cctv = np.ascontiguousarray(recs[: int(off[1])])
+    moving = random_frame(rng, 3000, 1920, 1080, 5)
+    static = cctv.copy()
+    static["src_x"], static["src_y"] = static["dst_x"], static["dst_y"]
+    half = cctv.copy()  # records that differ in ONE coordinate only, either one
+    half["src_x"] = half["dst_x"]
+    half["src_y"] = half["dst_y"] + (np.arange(len(half)) % 3 == 0)
+    assert 0 < len(_moving_mv8(cctv)) < len(cctv) and len(_moving_mv8(static)) == 0
+    for frame in (cctv, moving, static, half):
+        for n in (0, 1, 7, 8, 9, 15, 16, 17, 63, 64, 65, 1000, len(frame)):
+            if n > len(frame):
+                continue
+            sub = np.ascontiguousarray(frame[:n])
+            got = ms.compact_records(sub)
+            assert got.tobytes() == _moving_mv8(sub).tobytes(), n
+    # every alignment of the first record against a 64-byte line (the vector loop starts at the first record on a line),
+    # and a source that is not even 8-byte aligned
+    for shift in range(9):
+        sub = cctv[shift : shift + 700]
+        assert sub.flags["C_CONTIGUOUS"] and sub.ctypes.data == cctv.ctypes.data + 40 * shift
+        assert ms.compact_records(sub).tobytes() == _moving_mv8(np.ascontiguousarray(sub)).tobytes(), shift
+    raw = np.zeros(40 * 300 + 64, np.uint8)
+    start = (-raw.ctypes.data) % 8 + 4
+    raw[start : start + 40 * 300] = cctv[:300].view(np.uint8)
+    odd = np.empty(300, ms.MV8_DTYPE)
+    n_odd = C.c_uint64(0)
+    assert ms.lib().mscan_compact_records(raw.ctypes.data + start, 300, odd.ctypes.data, C.byref(n_odd)) == ms.OK
+    assert odd[: n_odd.value].tobytes() == _moving_mv8(np.ascontiguousarray(cctv[:300])).tobytes()
+    # per-frame form used by callers that compact into their own (pinned) buffer
+    cnt, off, recs, _ = ms.synth_host(ms.synth_preset(0, 3), 0, 12)
+    out, mcnt = ms.compact_frames(recs, off)
+    assert out.tobytes() == _moving_mv8(recs).tobytes()
+    assert [int(x) for x in mcnt] == [len(_moving_mv8(np.ascontiguousarray(recs[int(off[f]) : int(off[f + 1])]))) for f in range(12)]
+    # misaligned output is refused
+    n_out = C.c_uint64(0)
+    buf = np.zeros(8 * 4 + 4, np.uint8)
+    assert ms.lib().mscan_compact_records(recs.ctypes.data, 4, buf.ctypes.data + 4, C.byref(n_out)) == ms.ERR_INVALID
+
+
+def test_host_passes_agree_without_avx512():
+    """The portable versions of the three host passes (projection, static-elided form, compaction) write the same bytes
+    as the AVX-512 ones: a child process with MSCAN_NO_AVX512=1 prints digests that must equal this process's."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import hashlib, numpy as np, motionscan as ms
+cnt, off, recs, pts = ms.synth_host(ms.synth_preset(4, 5), 0, 6)
+h = hashlib.sha256()
+h.update(ms.pack_records(recs).tobytes())
+enc, eoff, te = ms.elide_frames(recs, off)
+h.update(np.asarray(enc).tobytes()); h.update(np.asarray(te).tobytes())
+out, mc = ms.compact_frames(recs, off)
+h.update(out.tobytes()); h.update(mc.tobytes())
+print(h.hexdigest())
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join(sys.path))
+    a = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip()
+    b = subprocess.run([sys.executable, "-c", code], env=dict(env, MSCAN_NO_AVX512="1"), capture_output=True, text=True, check=True).stdout.strip()
+    assert len(a) == 64 and a == b

@@ -9,6 +9,8 @@ Feed modes (include/motionscan.h, mscan_set_staging_mode / mscan_submit_packed):
   packed-pageable  caller-projected mscan_mv8 in pageable memory                   → K-A<packed>
   elided           native records in pageable memory, sent in the static-elided form (mode ELIDE) → K-A<mvz>
   elided-pinned    native records in pinned memory, same                           → K-A<mvz>
+  compact          native records in pageable memory, only the moving ones sent (mode COMPACT) → K-A<packed>
+  compact-pinned   native records in pinned memory, same                           → K-A<packed>
 """
 import numpy as np
 import pytest
@@ -19,7 +21,8 @@ import oracle_lib as orc
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["native-inplace", "native-staged", "projected", "projected-pinned", "packed-pinned", "packed-pageable", "elided", "elided-pinned"]
+MODES = ["native-inplace", "native-staged", "projected", "projected-pinned", "packed-pinned", "packed-pageable", "elided", "elided-pinned", "compact",
+         "compact-pinned"]
 
 
 def cfg_for(p, w, h):
@@ -33,7 +36,8 @@ class Feeder:
     def __init__(self, ctx, mode):
         self.ctx, self.mode, self.pinned = ctx, mode, []
         ctx.set_staging_mode({"native-staged": ms.STAGING_NATIVE, "projected-pinned": ms.STAGING_PACK, "elided": ms.STAGING_ELIDE,
-                              "elided-pinned": ms.STAGING_ELIDE}.get(mode, ms.STAGING_AUTO))
+                              "elided-pinned": ms.STAGING_ELIDE, "compact": ms.STAGING_COMPACT,
+                              "compact-pinned": ms.STAGING_COMPACT}.get(mode, ms.STAGING_AUTO))
 
     def _pin(self, a):
         h = self.ctx.pinned_array(max(len(a), 1), a.dtype)[: len(a)]
@@ -45,9 +49,9 @@ class Feeder:
         if recs is None:
             recs = np.zeros(0, ms.MV_DTYPE)
         m = self.mode
-        if m in ("native-inplace", "projected-pinned", "elided-pinned"):
+        if m in ("native-inplace", "projected-pinned", "elided-pinned", "compact-pinned"):
             return self.ctx.submit(vid, pts, cnt, self._pin(recs))
-        if m in ("native-staged", "projected", "elided"):
+        if m in ("native-staged", "projected", "elided", "compact"):
             return self.ctx.submit(vid, pts, cnt, recs)
         r8 = ms.pack_records(recs)
         return self.ctx.submit_packed(vid, pts, cnt, self._pin(r8) if m == "packed-pinned" else r8)
@@ -140,6 +144,12 @@ def test_synthetic_clip_every_feed_mode(mode):
     elif mode.startswith("elided"):
         assert 4 * n_rec <= st.h2d_bytes < 8 * n_rec  # static records travel as 4 bytes + a mask bit
         assert st.records_projected == n_rec == st.records_elided
+    elif mode.startswith("compact"):
+        r8 = ms.pack_records(recs)
+        n_moving = int(((r8["src_x"] != r8["dst_x"]) | (r8["src_y"] != r8["dst_y"])).sum())
+        assert st.records_projected == n_rec == st.records_elided and st.elided_bytes == 8 * n_moving
+        assert 8 * n_moving <= st.h2d_bytes < 8 * n_moving + 64 * n  # static records do not travel at all
+        assert st.records_scanned == n_moving
     else:
         assert 8 * n_rec <= st.h2d_bytes < 9 * n_rec  # 8 B/record + per-frame metadata cross PCIe
         assert st.records_projected == (n_rec if mode.startswith("projected") else 0)
@@ -348,3 +358,104 @@ def test_submit_elided_takes_the_callers_own_encoding(pinned):
         with pytest.raises(ms.MscanError) as e:
             ctx.submit_elided(9, pts[:2], cnt[:2], enc_pageable, enc_off[:3], te)
         assert e.value.code == ms.ERR_INVALID
+
+
+def test_compact_transport_sends_only_moving_records():
+    """MSCAN_STAGING_COMPACT on a CCTV-style clip: identical flags and counts with well under 1 B/record on the wire;
+    per-frame submits, then a multi-frame submit that spans several pieces and slabs, keep submission order."""
+    p = kats.env_params()
+    spec = ms.synth_preset(1, 2)
+    n = 400
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=4)
+    with ms.Context(0, p, 1 << 16, 1 << 20) as ctx:
+        ctx.set_staging_mode(ms.STAGING_COMPACT)
+        ctx.video_open(1, spec.width, spec.height)
+        for f in range(100):
+            assert ctx.submit(1, pts[f : f + 1], cnt[f : f + 1], recs[int(off[f]) : int(off[f + 1])]) == f
+        assert ctx.submit(1, pts[100:], cnt[100:], recs[int(off[100]) :]) == 100
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+    assert np.array_equal(flags, of) and np.array_equal(counts, oc) and of.any()
+    assert st.records_elided == int(off[-1]) == st.records_projected
+    assert st.elided_bytes / st.records_elided < 1.5
+
+
+@pytest.mark.parametrize("thr", [0.0, -1.0, float("nan"), 0.25, 1e300])
+def test_compact_mode_only_drops_what_cannot_vote(thr):
+    """Static records vote when MV_THRESHOLD_SQ <= 0 (or NaN): COMPACT and AUTO must then send them (static-elided
+    form); with any positive threshold — also one no int32 magnitude reaches — the compaction is exact."""
+    p = kats.env_params(vectors_needed=2)
+    p.mv_threshold_sq = thr
+    spec = ms.synth_preset(1, 8)
+    n = 60
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    cfg = cfg_for(p, spec.width, spec.height)
+    of, oc = orc.scan_frames(cfg, recs, off, threads=4)
+    for mode in (ms.STAGING_COMPACT, ms.STAGING_AUTO):
+        with ms.Context(0, p, 1 << 12, 8 << 20) as ctx:
+            ctx.set_staging_mode(mode)
+            ctx.video_open(1, spec.width, spec.height)
+            for f in range(n):
+                ctx.submit(1, pts[f : f + 1], cnt[f : f + 1], recs[int(off[f]) : int(off[f + 1])])
+            flags, counts = ctx.collect(1)
+            st = ctx.stats()
+        assert np.array_equal(flags, of) and np.array_equal(counts, oc), (thr, mode)
+        per_rec = st.elided_bytes / st.records_elided
+        assert (per_rec < 1.5) if thr > 0 else (per_rec >= 4.0), (thr, mode, per_rec)
+    if not thr > 0:
+        assert of.all() or oc.max() > 0  # static macroblocks really did vote here
+
+
+def test_compact_mode_feeds_the_cluster_kernel_too():
+    """Compacted records are plain mscan_mv8: grids beyond one CTA's shared memory (8K) take them like any packed submit."""
+    from test_oracle_kats import random_frame
+
+    p = kats.env_params(vectors_needed=2)
+    w, h = 7680, 4320
+    rng = np.random.default_rng(13)
+    frames = [random_frame(rng, 20000, w, h, 6) for _ in range(4)]
+    for f in frames:  # make two thirds of the records static
+        keep = np.arange(len(f)) % 3 != 0
+        f["src_x"][keep], f["src_y"][keep] = f["dst_x"][keep], f["dst_y"][keep]
+    cnt = np.array([len(f) for f in frames], np.uint32)
+    cfg = cfg_for(p, w, h)
+    with ms.Context(0, p) as ctx:
+        ctx.set_staging_mode(ms.STAGING_COMPACT)
+        ctx.video_open(1, w, h)
+        ctx.submit(1, np.arange(4) / 30.0, cnt, kats.cat(*frames))
+        flags, counts = ctx.collect(1)
+        st = ctx.stats()
+    assert list(counts) == [orc.full_count(cfg, f) for f in frames]
+    assert st.records_elided == int(cnt.sum()) and 0 < st.records_scanned < int(cnt.sum()) // 2
+
+
+def test_concurrent_multi_piece_compact_submits_keep_each_calls_frames_together():
+    """Two threads submit large COMPACT calls (several pieces each) to ONE video at the same time: every call's frames
+    occupy the contiguous index range that starts at its first_frame_out, in the call's own order."""
+    import threading
+
+    p = kats.env_params()
+    spec = ms.synth_preset(1, 17)
+    n = 240  # ~2.4 M records per call: about ten pieces of 256 Ki records
+    cnt, off, recs, pts = ms.synth_host(spec, 0, n)
+    of, oc = orc.scan_frames(cfg_for(p, spec.width, spec.height), recs, off, threads=8)
+    assert int(off[-1]) > 4 * (1 << 18)
+    with ms.Context(0, p, 1 << 14, 2 << 20) as ctx:
+        ctx.set_staging_mode(ms.STAGING_COMPACT)
+        ctx.video_open(1, spec.width, spec.height)
+        firsts = {}
+
+        def work(k):
+            for rep in range(2):
+                firsts[(k, rep)] = ctx.submit(1, pts + 100.0 * (2 * k + rep), cnt, recs)
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        flags, counts = ctx.collect(1)
+    assert sorted(firsts.values()) == [0, n, 2 * n, 3 * n]
+    for first in firsts.values():
+        assert np.array_equal(flags[first : first + n], of) and np.array_equal(counts[first : first + n], oc)
