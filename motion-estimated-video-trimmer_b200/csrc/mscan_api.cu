@@ -35,6 +35,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -67,16 +68,21 @@ struct Extent {
 };
 
 struct Video {
+  // (what every submit writes comes first: it shares cache lines that travel between the decode threads' cores)
   uint32_t geom = 0;
   uint64_t n_frames = 0;
-  std::vector<Extent> extents;
   // epoch of each slab when this video last put frames into it: equal to the slab's current epoch ⇔ results
   // of this video may still be pending there (what collect / segments / close have to wait for — nothing else)
   uint64_t slab_epoch[kSlabs] = {0, 0, 0};
+  // host-pass counters of this video's compacted submits, kept here because the submit's critical section writes this
+  // node anyway; folded into the context's stats by fold_stats / mscan_video_close
+  uint64_t st_records = 0, st_wire_bytes = 0, st_ns = 0;
+  std::vector<Extent> extents;
   uint64_t dev_seq = 0;  // mscan_submit_device: sequence number of this video's last launch on the context's dev_stream
 };
 
 struct Slab {
+  // ---- set up once (read-mostly) ----
   uint8_t* d_recs = nullptr;
   uint8_t* h_recs = nullptr;  // pinned, allocated on first pageable submit
   uint64_t* d_rec_off = nullptr;
@@ -87,31 +93,33 @@ struct Slab {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   cudaEvent_t copied = nullptr;  // recorded after the slab's last H2D copy (mscan_host_fence)
-  bool in_flight = false;
-  uint64_t bytes = 0;   // fill level of d_recs (and of h_recs, which mirrors its offsets)
-  uint32_t frames = 0;  // frames staged since the slab was recycled
-  // The open segment = frames [seg_frame0, frames): one record format, one K-A launch. A slab carries any
-  // number of segments (chunk workers may feed different formats); they are launched in order on `stream`.
-  uint8_t fmt = 0;            // record layout of the open segment: kLayoutNative (40 B), kLayoutMv8 (8 B) or kLayoutMvz
   // mvz segments: tile directory (start of every tile in 16-byte units from the segment base, + the end of the last)
   // and each frame's first tile; a segment of k tiles uses k + 1 directory slots
   uint32_t *d_tile_dir = nullptr, *h_tile_dir = nullptr, *d_frame_tile0 = nullptr, *h_frame_tile0 = nullptr;
-  uint32_t dir_slots = 0;     // directory slots used since the slab was recycled
-  uint32_t seg_dir0 = 0;      // first directory slot of the open segment
+  std::unique_ptr<std::atomic<int32_t>[]> pend;  // per copy window: uncommitted reservations that touch it
+  // ---- what every reservation reads and writes: one cache line (it travels between the decode threads' cores) ----
+  // The open segment = frames [seg_frame0, frames): one record format, one K-A launch. A slab carries any
+  // number of segments (chunk workers may feed different formats); they are launched in order on `stream`.
+  alignas(64) uint64_t bytes = 0;        // fill level of d_recs (and of h_recs, which mirrors its offsets)
+  uint64_t seg_recs = 0;
+  std::atomic<uint64_t> reserved_end{0};  // == bytes, published for the copy pump
+  uint64_t epoch = 1;                     // bumped by every recycle
+  uint32_t frames = 0;                    // frames staged since the slab was recycled
   uint32_t seg_frame0 = 0;
   uint32_t seg_slot0 = 0;     // first rec_off slot of the open segment (a segment of k frames uses k+1 slots)
-  uint64_t seg_byte0 = 0;     // 256-byte aligned offset of the open segment's first record
-  uint64_t seg_recs = 0;
-  uint64_t seg_log_base = 0;  // frame-log index of the open segment's first frame
-  // ---- concurrent fill (reserve under ctx->mu, fill outside, commit with atomics) ----
-  bool staged = false;                 // the open segment's records pass through h_recs (else DMA'd from caller memory)
-  uint64_t epoch = 1;                  // bumped by every recycle
+  uint32_t dir_slots = 0;     // directory slots used since the slab was recycled
+  uint32_t seg_dir0 = 0;      // first directory slot of the open segment
+  uint8_t fmt = 0;            // record layout of the open segment: kLayoutNative (40 B), kLayoutMv8 (8 B) or kLayoutMvz
+  bool staged = false;        // the open segment's records pass through h_recs (else DMA'd from caller memory)
+  bool in_flight = false;
+  // ---- per segment / per launch ----
+  alignas(64) uint64_t seg_byte0 = 0;  // 256-byte aligned offset of the open segment's first record
+  uint64_t seg_log_base = 0;           // frame-log index of the open segment's first frame
   uint64_t launch_seq = 0;             // bumped by every K-A launch on this slab
-  std::atomic<uint32_t> writers{0};    // reservations of the open segment whose fill has not been committed
-  std::unique_ptr<std::atomic<int32_t>[]> pend;  // per copy window: uncommitted reservations that touch it
-  std::atomic<uint64_t> reserved_end{0};         // == bytes, published for the copy pump
   uint64_t copy_head = 0;              // (ctx->issue_mu) staged bytes of the open segment below this are on their way
+  std::atomic<uint32_t> writers{0};    // in-place reservations of the open segment whose copy has not been enqueued
 };
+static_assert(offsetof(Slab, in_flight) / 64 == offsetof(Slab, bytes) / 64, "the reservation fields of a slab share one cache line");
 
 struct EvPair {
   cudaEvent_t a, b;
@@ -311,7 +319,12 @@ struct mscan_ctx {
   // Lock order: tail_mu → mu → issue_mu. `mu` guards the bookkeeping (videos, frame log, slab fill levels) and is
   // never held while records are projected or copied; `issue_mu` orders the H2D copies of staged windows with the
   // K-A launch that consumes them; `tail_mu` serialises K-C (its scratch and main_stream) without blocking submits.
-  std::mutex mu, issue_mu, tail_mu;
+  // `mu` shares its cache line with what every reservation updates under it (taking the lock brings them along)
+  alignas(64) std::mutex mu;
+  int cur = 0;                           // slab of the ring that is being filled
+  uint64_t log_head = 0, log_limit = 0;  // frames [log_head, log_limit) of the log are known to be free (space closed videos gave back is found on demand)
+  alignas(64) std::mutex issue_mu;
+  std::mutex tail_mu;
   std::string err;
 
   // kernel constants derived from params
@@ -328,8 +341,7 @@ struct mscan_ctx {
   ScanPlan plan_packed{};  // mscan_mv8 slabs
 
   // frame log
-  uint64_t log_cap = 0, log_head = 0;
-  uint64_t log_limit = 0;  // frames [log_head, log_limit) are known to be free (space closed videos gave back is found on demand)
+  uint64_t log_cap = 0;
   double* d_pts = nullptr;
   uint8_t* d_flags = nullptr;
   uint32_t* d_counts = nullptr;
@@ -339,7 +351,6 @@ struct mscan_ctx {
   uint32_t slab_frames = 0;
   uint32_t slab_dir_cap = 0;  // tile-directory slots per slab
   Slab slabs[kSlabs];
-  int cur = 0;
 
   uint32_t* d_work = nullptr;  // kWorkSlots × {next, done}
   uint32_t work_rr = 0;
@@ -431,7 +442,16 @@ int fail(mscan_ctx* c, int code, const char* fmt, ...) {
 }
 
 // folds the counters that are written outside `mu` into the public stats (caller holds mu)
+void fold_video_stats(mscan_ctx* c, Video& v) {
+  c->stats.records_projected += v.st_records;
+  c->stats.records_elided += v.st_records;
+  c->stats.elided_bytes += v.st_wire_bytes;
+  c->stats.project_ms += (double)v.st_ns * 1e-6;
+  v.st_records = v.st_wire_bytes = v.st_ns = 0;
+}
+
 void fold_stats(mscan_ctx* c) {
+  for (auto& kv : c->videos) fold_video_stats(c, kv.second);
   c->stats.h2d_bytes += c->a_h2d_bytes.exchange(0, std::memory_order_relaxed);
   c->stats.records_projected += c->a_records_projected.exchange(0, std::memory_order_relaxed);
   c->stats.project_ms += (double)c->a_project_ns.exchange(0, std::memory_order_relaxed) * 1e-6;
@@ -1674,10 +1694,9 @@ static int submit_impl(mscan_ctx* c, uint32_t video_id, uint32_t n_frames, const
     span->have = true;
   }
   if (span->st_records) {
-    c->stats.records_projected += span->st_records;
-    c->stats.records_elided += span->st_records;
-    c->stats.elided_bytes += span->st_wire_bytes;
-    c->stats.project_ms += (double)span->st_ns * 1e-6;
+    it->second.st_records += span->st_records;
+    it->second.st_wire_bytes += span->st_wire_bytes;
+    it->second.st_ns += span->st_ns;
     span->st_records = 0;
   }
   const uint64_t vbase = span->vbase + span->f0;
@@ -2348,6 +2367,7 @@ int mscan_video_close(mscan_ctx* c, uint32_t video_id) try {
   if (rc) return rc;
   auto it = c->videos.find(video_id);
   if (it == c->videos.end()) return MSCAN_OK;  // closed by another thread while we waited
+  fold_video_stats(c, it->second);
   c->videos.erase(it);
   if (c->videos.empty()) {  // nothing live any more: rewind
     c->log_head = 0;
