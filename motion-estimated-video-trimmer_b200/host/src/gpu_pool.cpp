@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <string>
 #include <thread>
 
 #include "motion_trim/config.hpp"
@@ -47,6 +48,14 @@ bool GpuPool::open(int max_gpus) {
     }
   }
   ctx_ = made;
+  // MOTION_TRIM_STAGING (experiments; not a reference knob): how mscan_submit moves the workers' records, see
+  // mscan_set_staging_mode. Unset = the library's default.
+  if (const char* st = std::getenv("MOTION_TRIM_STAGING")) {
+    const std::string v(st);
+    const int mode = v == "pack" ? MSCAN_STAGING_PACK : v == "native" ? MSCAN_STAGING_NATIVE : v == "elide" ? MSCAN_STAGING_ELIDE
+                     : v == "compact" ? MSCAN_STAGING_COMPACT : MSCAN_STAGING_AUTO;
+    for (mscan_ctx* c : ctx_) mscan_set_staging_mode(c, mode);
+  }
   // (the library's projection pool is one per process, shared by these contexts: nothing to size per GPU)
   return true;
 }

@@ -72,7 +72,8 @@ def main():
             env0["MSCAN_TRACE"] = "1"
         # default: the mapped file is pinned and DMA'd in place (40 B/record over PCIe, no host pass); nopin: the chunk
         # workers project their chunks into the library's pinned ring (8 B/record over PCIe); populate: MAP_POPULATE
-        for mode, extra in (("default", {}), ("nopin", {"MOTION_TRIM_NO_PIN": "1"}), ("populate", {"MOTION_TRIM_POPULATE": "1"})):
+        for mode, extra in (("default", {}), ("nopin", {"MOTION_TRIM_NO_PIN": "1"}), ("populate", {"MOTION_TRIM_POPULATE": "1"}),
+                            ("compact", {"MOTION_TRIM_NO_PIN": "1", "MOTION_TRIM_STAGING": "compact"})):
             if mode not in args.modes.split(","):
                 continue
             outd = Path(args.dir) / f"out_{g}_{mode}"
