@@ -342,24 +342,39 @@ __attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) uint64_t compact
   const __m512i ia = _mm512_load_si512(t.a), ib = _mm512_load_si512(t.b), ic = _mm512_load_si512(t.c);
   const __mmask64 mb = t.mask_b, mc = t.mask_c;
   const uint64_t blocks = n / 8;
-  for (uint64_t g = 0; g < blocks; ++g) {
-    const uint8_t* p = in + 320 * g;
-    _mm_prefetch(reinterpret_cast<const char*>(p + 4096), _MM_HINT_T0);
-    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 64), _MM_HINT_T0);
-    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 128), _MM_HINT_T0);
-    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 192), _MM_HINT_T0);
-    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 256), _MM_HINT_T0);
-    const __m512i z0 = _mm512_load_si512(p), z1 = _mm512_load_si512(p + 64), z2 = _mm512_load_si512(p + 128),
-                  z3 = _mm512_load_si512(p + 192), z4 = _mm512_load_si512(p + 256);
-    __m512i v = _mm512_permutex2var_epi8(z0, ia, z1);
-    v = _mm512_mask_mov_epi8(v, mb, _mm512_permutex2var_epi8(z2, ib, z3));
-    v = _mm512_mask_permutexvar_epi8(v, mc, ic, z4);  // 8 records: src | dst << 32
-    const __mmask8 k = _mm512_cmpneq_epi64_mask(v, _mm512_rol_epi64(v, 32));  // halves differ ⇔ moving
-    if (k) {
-      _mm512_storeu_si512(out + m, _mm512_maskz_compress_epi64(k, v));  // (a whole register: at most 8 g records precede it, so it ends inside out[n))
-      m += (uint64_t)__builtin_popcount((unsigned)k);
-    }
+  // One step: 8 records → mask of the moving ones. Where moving records are rare and clustered (CCTV: quiet areas, a few
+  // objects) the compress + store are skipped with a well-predicted branch; where they are scattered (10 % uniformly in
+  // the SURVEY §8(d) stream: 57 % of the steps hold one, at random) that branch mispredicts every other step and doubles
+  // the cost of the pass (profiles/r03_bench_stream1e9_spec.json before/after), so stretches of 64 steps that held more
+  // than 8 moving records are followed by a stretch without the branch.
+#define MSCAN_COMPACT_STEP(BRANCH)                                                                                     \
+  {                                                                                                                    \
+    const uint8_t* p = in + 320 * g;                                                                                   \
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096), _MM_HINT_T0);                                                \
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 64), _MM_HINT_T0);                                           \
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 128), _MM_HINT_T0);                                          \
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 192), _MM_HINT_T0);                                          \
+    _mm_prefetch(reinterpret_cast<const char*>(p + 4096 + 256), _MM_HINT_T0);                                          \
+    const __m512i z0 = _mm512_load_si512(p), z1 = _mm512_load_si512(p + 64), z2 = _mm512_load_si512(p + 128),          \
+                  z3 = _mm512_load_si512(p + 192), z4 = _mm512_load_si512(p + 256);                                    \
+    __m512i v = _mm512_permutex2var_epi8(z0, ia, z1);                                                                  \
+    v = _mm512_mask_mov_epi8(v, mb, _mm512_permutex2var_epi8(z2, ib, z3));                                             \
+    v = _mm512_mask_permutexvar_epi8(v, mc, ic, z4); /* 8 records: src | dst << 32 */                                  \
+    const __mmask8 k = _mm512_cmpneq_epi64_mask(v, _mm512_rol_epi64(v, 32)); /* halves differ ⇔ moving */              \
+    if (!(BRANCH) || k) {                                                                                              \
+      /* a whole register: at most 8 g records precede it, so it ends inside out[n) */                                 \
+      _mm512_storeu_si512(out + m, _mm512_maskz_compress_epi64(k, v));                                                 \
+      m += (uint64_t)__builtin_popcount((unsigned)k);                                                                  \
+    }                                                                                                                  \
   }
+  bool scattered = false;
+  for (uint64_t g = 0; g < blocks;) {
+    const uint64_t g_end = g + 64 < blocks ? g + 64 : blocks, m0 = m;
+    if (scattered) for (; g < g_end; ++g) MSCAN_COMPACT_STEP(false)
+    else for (; g < g_end; ++g) MSCAN_COMPACT_STEP(true)
+    scattered = m - m0 > 8;
+  }
+#undef MSCAN_COMPACT_STEP
   return m + compact_scalar(in + 320 * blocks, n - 8 * blocks, out + m);
 }
 #endif

@@ -234,6 +234,17 @@ def test_compaction_keeps_exactly_the_moving_records_in_order():
     n_odd = C.c_uint64(0)
     assert ms.lib().mscan_compact_records(raw.ctypes.data + start, 300, odd.ctypes.data, C.byref(n_odd)) == ms.OK
     assert odd[: n_odd.value].tobytes() == _moving_mv8(np.ascontiguousarray(cctv[:300])).tobytes()
+    # scattered moving records (the SURVEY §8(d) stream: 10 % at random) and frames that alternate between quiet and busy
+    # stretches: the vector loop switches between its two step forms every 64 steps
+    _, soff, srecs, _ = ms.synth_host(ms.synth_preset(5, 5), 0, 3)
+    assert ms.compact_records(srecs).tobytes() == _moving_mv8(srecs).tobytes()
+    mix = np.ascontiguousarray(srecs[:16000]).copy()
+    for a in range(0, 16000, 3000):  # quiet stretches of 1500 records
+        mix["src_x"][a : a + 1500], mix["src_y"][a : a + 1500] = mix["dst_x"][a : a + 1500], mix["dst_y"][a : a + 1500]
+    busy = np.arange(16000) % 3000 >= 2200  # and stretches where everything moves
+    mix["src_x"][busy] = mix["dst_x"][busy] + 1
+    for shift in (0, 3):
+        assert ms.compact_records(mix[shift:]).tobytes() == _moving_mv8(np.ascontiguousarray(mix[shift:])).tobytes()
     # per-frame form used by callers that compact into their own (pinned) buffer
     cnt, off, recs, _ = ms.synth_host(ms.synth_preset(0, 3), 0, 12)
     out, mcnt = ms.compact_frames(recs, off)

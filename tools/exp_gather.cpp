@@ -87,6 +87,25 @@ TGT_A static uint64_t compactC(const uint8_t* in, uint64_t n, uint64_t* out) {
   }
   return m + compact_scalar(in + 320 * g, n - 8 * g, out + m);
 }
+TGT_A static uint64_t compactD(const uint8_t* in, uint64_t n, uint64_t* out) {
+  const __m512i ia = _mm512_load_si512(T.a), ib = _mm512_load_si512(T.b), ic = _mm512_load_si512(T.c);
+  uint64_t head = (((64 - (reinterpret_cast<uintptr_t>(in) & 63)) & 63) / 8 * 5) & 7;
+  if ((reinterpret_cast<uintptr_t>(in) & 7) || head > n) head = n < 8 ? n : 0;
+  uint64_t m = compact_scalar(in, head, out);
+  in += 40 * head; n -= head;
+  const bool al = (reinterpret_cast<uintptr_t>(in) & 63) == 0;
+  uint64_t g = 0;
+  if (al) for (; g < n / 8; ++g) {
+    const uint8_t* p = in + 320 * g;
+    const __m512i z0 = _mm512_load_si512(p), z1 = _mm512_load_si512(p + 64), z2 = _mm512_load_si512(p + 128), z3 = _mm512_load_si512(p + 192), z4 = _mm512_load_si512(p + 256);
+    __m512i v = _mm512_permutex2var_epi8(z0, ia, z1);
+    v = _mm512_mask_mov_epi8(v, T.mb, _mm512_permutex2var_epi8(z2, ib, z3));
+    v = _mm512_mask_permutexvar_epi8(v, T.mc, ic, z4);
+    const __mmask8 k = _mm512_cmpneq_epi64_mask(v, _mm512_rol_epi64(v, 32));
+    _mm512_storeu_si512(out + m, _mm512_maskz_compress_epi64(k, v)); m += __builtin_popcount((unsigned)k);
+  }
+  return m + compact_scalar(in + 320 * g, n - 8 * g, out + m);
+}
 TGT_A static uint64_t projectA(const uint8_t* in, uint64_t n, uint64_t* out) {
   const __m512i ia = _mm512_load_si512(T.a), ib = _mm512_load_si512(T.b), ic = _mm512_load_si512(T.c);
   for (uint64_t g = 0; g < n / 8; ++g) _mm512_storeu_si512(out + 8 * g, gatherA(in + 320 * g, ia, ib, ic));
@@ -102,7 +121,8 @@ int main(int argc, char** argv) {
   init_tables();
   const size_t n = argc > 1 ? atol(argv[1]) : 10000;
   const int maxT = argc > 2 ? atoi(argv[2]) : (int)std::thread::hardware_concurrency();
-  struct V { const char* name; Fn f; } vs[] = {{"compact A (vbmi permutes)", compactA}, {"compact B (masked loads) ", compactB}, {"compact C (A, input peeled)", compactC}, {"project A (vbmi permutes)", projectA}, {"project B (masked loads) ", projectB}};
+  const int uniform_pct = argc > 3 ? atoi(argv[3]) : 0;  // 0: one moving record in 40, regularly; else: that percentage, scattered
+  struct V { const char* name; Fn f; } vs[] = {{"compact A (vbmi permutes)", compactA}, {"compact B (masked loads) ", compactB}, {"compact C (A, input peeled)", compactC}, {"compact D (C, branchless)   ", compactD}, {"project A (vbmi permutes)", projectA}, {"project B (masked loads) ", projectB}};
   for (int threads : {1, maxT / 2, maxT}) {
     if (threads < 1) continue;
     for (int shift : {0, 24}) {
@@ -119,7 +139,12 @@ int main(int argc, char** argv) {
               uint8_t* buf = (uint8_t*)aligned_alloc(64, 40 * n + 256);
               for (size_t i = 0; i < 40 * n + 256; ++i) buf[i] = (uint8_t)(i * 7 + t);
               uint8_t* in = buf + shift;
-              for (size_t r = 0; r < n; ++r) if (r % 40) memcpy(in + 40 * r + 6, in + 40 * r + 10, 4);
+              uint64_t lcg = 88172645463325252ull + t;
+              for (size_t r = 0; r < n; ++r) {
+                lcg ^= lcg << 13; lcg ^= lcg >> 7; lcg ^= lcg << 17;
+                const bool moving = uniform_pct ? (int)(lcg % 100) < uniform_pct : (r % 40) == 0;
+                if (!moving) memcpy(in + 40 * r + 6, in + 40 * r + 10, 4);
+              }
               std::vector<uint64_t> out(n + 16);
               volatile uint64_t sink = 0;
               for (int i = 0; i < 50; ++i) sink += v.f(in, n, out.data());
