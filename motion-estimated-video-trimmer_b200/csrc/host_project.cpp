@@ -345,7 +345,7 @@ __attribute__((target("avx512f,avx512bw,avx512vl,avx512vbmi"))) uint64_t compact
   // One step: 8 records → mask of the moving ones. Where moving records are rare and clustered (CCTV: quiet areas, a few
   // objects) the compress + store are skipped with a well-predicted branch; where they are scattered (10 % uniformly in
   // the SURVEY §8(d) stream: 57 % of the steps hold one, at random) that branch mispredicts every other step and doubles
-  // the cost of the pass (profiles/r03_bench_stream1e9_spec.json before/after), so stretches of 64 steps that held more
+  // the cost of the pass (profiles/r03_bench_stream1e9_spec.json → …_spec_after.json: 56 → 28 ms per 60 M records), so stretches of 64 steps that held more
   // than 8 moving records are followed by a stretch without the branch.
 #define MSCAN_COMPACT_STEP(BRANCH)                                                                                     \
   {                                                                                                                    \
